@@ -1,0 +1,183 @@
+/*
+ * rgs_b200.h -- C ABI of the B200-native differentiable Gaussian-splat rasterizer.
+ *
+ * This is the drop-in boundary of the hot path.  The reference binds the same path through a pybind11
+ * torch extension (`diff_gaussian_rasterization._C`, reference: submodules/diff-gaussian-rasterization/
+ * ext.cpp:15-20, rasterize_points.h:18-81) whose C++ core is CudaRasterizer::Rasterizer
+ * (cuda_rasterizer/rasterizer.h:25-149).  The entry points below are what that core exposes, restated
+ * as a plain C ABI: raw device pointers, sizes and a cudaStream_t, no torch types.  The torch glue in
+ * rade-gs_b200/csrc/torch_glue.cpp is the only caller in the product and rebuilds the reference's four
+ * pybind symbols on top of it.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; optional inputs are NULL when absent
+ *     (the reference passes empty tensors whose data pointer is null, rasterize_points.cu:104-112);
+ *   - matrices are 16 floats in the memory order torch hands over (`world_view_transform`, i.e.
+ *     column-major of the maths matrix, cuda_rasterizer/auxiliary.h:74-93);
+ *   - scratch memory is obtained through caller-supplied resize callbacks, exactly like the reference's
+ *     std::function<char*(size_t)> geometry/binning/image buffers (cuda_rasterizer/rasterizer.h:31-35);
+ *     their CONTENT is private to this library, the caller only keeps them alive between forward and
+ *     backward and hands the same bytes back;
+ *   - functions return >= 0 on success (rgs_forward: num_rendered) and a negative rgs_status on error;
+ *     rgs_last_error() gives the message of the last failure on the calling thread.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with RGS_E_CUDA.
+ */
+#ifndef RGS_B200_H_INCLUDED
+#define RGS_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGS_ABI_VERSION 1
+
+typedef enum rgs_status {
+	RGS_OK = 0,
+	RGS_E_INVALID = -1,      /* bad argument (shape/flag combination the reference rejects)            */
+	RGS_E_CUDA = -2,         /* CUDA runtime error (message in rgs_last_error)                         */
+	RGS_E_UNSUPPORTED = -3,  /* e.g. prefiltered=true (mis-wired in the reference)    */
+	RGS_E_ALLOC = -4         /* a resize callback returned NULL                                        */
+} rgs_status;
+
+/* Resize callback: make the buffer at least `bytes` long and return its device address.
+ * Mirrors cuda_rasterizer/rasterizer.h:31-33 / rasterize_points.cu:27-33 (resizeFunctional). */
+typedef char* (*rgs_resize_fn)(void* user, size_t bytes);
+
+/* Camera + raster settings shared by forward and backward
+ * (GaussianRasterizationSettings, diff_gaussian_rasterization/__init__.py:171-186). */
+typedef struct rgs_camera {
+	int32_t width, height;
+	float tan_fovx, tan_fovy;
+	float kernel_size;       /* 2D mip filter added to the cov2D diagonal (forward.cu:116-118)       */
+	float scale_modifier;
+	const float* viewmatrix; /* [16] */
+	const float* projmatrix; /* [16] */
+	const float* cam_pos;    /* [3]  */
+	const float* background; /* [3]  */
+	int32_t sh_degree;       /* active degree D                                                        */
+	int32_t sh_coeffs;       /* M = coefficients stored per Gaussian (0 when shs == NULL)              */
+	int32_t require_coord, require_depth, prefiltered, debug;
+	/* Tile-row slab rendered by this call: tile rows [tile_row_begin, tile_row_end).  (0, -1) = whole
+	 * image.  Multi-GPU row sharding (DESIGN.md "Multi-GPU"); the reference has no equivalent.       */
+	int32_t tile_row_begin, tile_row_end;
+} rgs_camera;
+
+/* Per-Gaussian model inputs (rasterize_points.h:18-41). */
+typedef struct rgs_gaussians {
+	int32_t P;
+	const float* means3D;        /* [P,3]                       */
+	const float* opacities;      /* [P]                         */
+	const float* shs;            /* [P,M,3] or NULL             */
+	const float* colors_precomp; /* [P,3]   or NULL             */
+	const float* scales;         /* [P,3]   or NULL             */
+	const float* rotations;      /* [P,4]   or NULL (r,x,y,z)   */
+	const float* cov3D_precomp;  /* [P,6]   or NULL             */
+} rgs_gaussians;
+
+/* Forward outputs (rasterize_points.cu:71-78); maps of a variant that is switched off are zero-filled. */
+typedef struct rgs_forward_out {
+	float* out_color;  /* [3,H,W] */
+	float* out_coord;  /* [3,H,W] */
+	float* out_mcoord; /* [3,H,W] */
+	float* out_alpha;  /* [1,H,W] */
+	float* out_normal; /* [3,H,W] */
+	float* out_depth;  /* [1,H,W] */
+	float* out_mdepth; /* [1,H,W] */
+	int32_t* radii;    /* [P]     */
+} rgs_forward_out;
+
+typedef struct rgs_buffers {
+	rgs_resize_fn geom;    void* geom_user;
+	rgs_resize_fn binning; void* binning_user;
+	rgs_resize_fn image;   void* image_user;
+} rgs_buffers;
+
+/* Replaces CudaRasterizer::Rasterizer::forward (rasterizer.h:25-66, rasterizer_impl.cu:254-425).
+ * Returns num_rendered (>= 0) or a negative rgs_status.  One stream synchronisation inside (the
+ * reference has the same blocking read of num_rendered, rasterizer_impl.cu:354). */
+int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* g, const rgs_forward_out* out,
+                    const rgs_buffers* bufs, void* cuda_stream);
+
+/* Upstream gradients of the seven maps (rasterize_points.h:57-63) + forward results read by backward. */
+typedef struct rgs_backward_in {
+	const float* dL_dout_color;  /* [3,H,W] */
+	const float* dL_dout_coord;  /* [3,H,W] */
+	const float* dL_dout_mcoord; /* [3,H,W] */
+	const float* dL_dout_depth;  /* [1,H,W] */
+	const float* dL_dout_mdepth; /* [1,H,W] */
+	const float* dL_dout_alpha;  /* [1,H,W] */
+	const float* dL_dout_normal; /* [3,H,W] */
+	const float* out_alpha;      /* forward's alpha map  [1,H,W] */
+	const float* out_normal;     /* forward's normal map [3,H,W] */
+	const int32_t* radii;        /* [P] */
+	const char* geom_buffer;     /* bytes written by rgs_forward */
+	const char* binning_buffer;
+	const char* image_buffer;
+	int64_t num_rendered;
+} rgs_backward_in;
+
+/* Final gradients (rasterize_points.cu:180-193,245).  All are fully written (zeros for Gaussians that
+ * were not rendered); the caller does not need to clear them. */
+typedef struct rgs_backward_out {
+	float* dL_dmeans2D;   /* [P,3] (x, y, |.| channel, backward.cu:1002-1006) */
+	float* dL_dcolors;    /* [P,3] */
+	float* dL_dopacity;   /* [P]   */
+	float* dL_dmeans3D;   /* [P,3] */
+	float* dL_dcov3D;     /* [P,6] */
+	float* dL_dsh;        /* [P,M,3] or NULL when M == 0 */
+	float* dL_dscales;    /* [P,3] */
+	float* dL_drotations; /* [P,4] */
+} rgs_backward_out;
+
+/* Floats per Gaussian of the screen-space gradient accumulator for a variant (16 or 32). */
+int32_t rgs_grad_stride(int32_t require_coord, int32_t require_depth);
+
+/* Stage 1 of backward: replaces BACKWARD::render (backward.cu:631-1016).  Zero-fills and accumulates
+ * grad_accum[P * rgs_grad_stride] with the per-Gaussian screen-space gradients of this call's tile slab.
+ * The accumulator is a plain sum over pixels, hence additive across slabs/ranks: multi-GPU callers
+ * all-reduce it between stage 1 and stage 2. */
+int32_t rgs_backward_render(const rgs_camera* cam, const rgs_gaussians* g, const rgs_backward_in* in,
+                            float* grad_accum, void* cuda_stream);
+
+/* Stage 2: replaces BACKWARD::preprocess (backward.cu:145-628): grad_accum -> parameter gradients. */
+int32_t rgs_backward_preprocess(const rgs_camera* cam, const rgs_gaussians* g, const rgs_backward_in* in,
+                                const float* grad_accum, const rgs_backward_out* out, void* cuda_stream);
+
+/* Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:110-148, rasterizer_impl.cu:429-571):
+ * stage 1 + stage 2 with an internally allocated accumulator (scratch through `grad_scratch`). */
+int32_t rgs_backward(const rgs_camera* cam, const rgs_gaussians* g, const rgs_backward_in* in,
+                     const rgs_backward_out* out, rgs_resize_fn grad_scratch, void* grad_scratch_user,
+                     void* cuda_stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:18-23, rasterizer_impl.cu:176-188). */
+int32_t rgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                         uint8_t* present, void* cuda_stream);
+
+/* Introspection for parity tests: views into the private buffers written by rgs_forward
+ * (the reference keeps the same data at BinningState::point_list / ImageState::ranges,
+ * rasterizer_impl.cu:237-250,224-235).  Pointers are device addresses inside the given buffers. */
+typedef struct rgs_debug_views {
+	const uint32_t* point_list;      /* [num_rendered] sorted Gaussian ids                 */
+	const uint64_t* point_list_keys; /* [num_rendered] sorted (tile<<32 | depth bits) keys */
+	const uint32_t* tile_ranges;     /* [tiles][2]  start,end                              */
+	const uint32_t* n_contrib;       /* [2,H,W] last contributor, median contributor       */
+	const uint32_t* tiles_touched;   /* [P]                                                */
+	const float* records;            /* [P, record_floats] packed render records           */
+	int32_t record_floats;
+	const float* depths;             /* [P] view-space z                                   */
+} rgs_debug_views;
+int32_t rgs_debug_get_views(const rgs_camera* cam, int32_t P, int64_t num_rendered, const char* geom_buffer,
+                            const char* binning_buffer, const char* image_buffer, rgs_debug_views* views);
+
+const char* rgs_last_error(void);
+int32_t rgs_abi_version(void);
+/* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
+int64_t rgs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGS_B200_H_INCLUDED */

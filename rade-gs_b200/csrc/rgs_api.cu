@@ -1,0 +1,288 @@
+// rgs_api.cu -- the C ABI (include/rgs_b200.h): buffer carving, orchestration, error handling.
+//
+// Replaces CudaRasterizer::Rasterizer::{forward,backward,markVisible} and the GeometryState /
+// BinningState / ImageState chunk allocator (reference: cuda_rasterizer/rasterizer_impl.cu:190-250,
+// 254-425, 429-571, 176-188; cuda_rasterizer/rasterizer_impl.h:22-94).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "rgs_common.cuh"
+
+namespace rgs {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static thread_local std::string t_error;
+
+static int fail(int code, const std::string& msg) {
+	t_error = msg;
+	return code;
+}
+
+#define RGS_CUDA_TRY(expr)                                                                                   \
+	do {                                                                                                     \
+		cudaError_t _e = (expr);                                                                             \
+		if (_e != cudaSuccess) return fail(RGS_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+	} while (0)
+
+// After each stage in debug mode: synchronise and surface the error, like CHECK_CUDA (auxiliary.h:404-411).
+static int debug_sync(const rgs_camera* cam, cudaStream_t s, const char* stage) {
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess && cam->debug) e = cudaStreamSynchronize(s);
+	if (e != cudaSuccess) return fail(RGS_E_CUDA, std::string("[CUDA ERROR] in ") + stage + ": " + cudaGetErrorString(e));
+	return RGS_OK;
+}
+
+static GeomView carve_geom(char* base, int P, bool coord, size_t scan_bytes, size_t* total) {
+	Carver c(base);
+	GeomView g;
+	g.records = c.take<float>((size_t)P * rec_floats(coord));
+	g.depths = c.take<float>(P);
+	g.tiles_touched = c.take<uint32_t>(P);
+	g.offsets = c.take<uint32_t>(P);
+	g.clamped = c.take<uint8_t>(P);
+	g.scan_temp = c.take<char>(scan_bytes);
+	g.scan_temp_bytes = scan_bytes;
+	if (total) *total = c.size();
+	return g;
+}
+
+static BinView carve_bin(char* base, size_t R, size_t sort_bytes, size_t* total) {
+	Carver c(base);
+	BinView b;
+	b.point_list = c.take<uint32_t>(R);
+	b.keys_sorted = c.take<uint64_t>(R);
+	b.point_list_unsorted = c.take<uint32_t>(R);
+	b.keys_unsorted = c.take<uint64_t>(R);
+	b.sort_temp = c.take<char>(sort_bytes);
+	b.sort_temp_bytes = sort_bytes;
+	if (total) *total = c.size();
+	return b;
+}
+
+static ImgView carve_img(char* base, int tiles, size_t N, bool coord, bool depth, size_t* total) {
+	Carver c(base);
+	ImgView v;
+	v.ranges = c.take<uint2>(tiles);
+	v.n_contrib = c.take<uint32_t>(2 * N);
+	v.accum_depth = c.take<float>(depth ? N : 0);
+	v.normal_length = c.take<float>((coord || depth) ? N : 0);
+	v.accum_coord = c.take<float>(coord ? 3 * N : 0);
+	if (total) *total = c.size();
+	return v;
+}
+
+static int make_params(const rgs_camera* cam, const rgs_gaussians* g, FwdParams& p) {
+	if (!cam || !g) return fail(RGS_E_INVALID, "null camera / gaussians");
+	if (cam->width <= 0 || cam->height <= 0) return fail(RGS_E_INVALID, "image size must be positive");
+	if (g->P < 0) return fail(RGS_E_INVALID, "negative Gaussian count");
+	if (cam->prefiltered)
+		return fail(RGS_E_UNSUPPORTED,
+		            "prefiltered=True is mis-wired in the reference (rasterizer_impl.cu:343-345 feeds it to the `integrate` switch) and is not supported");
+	const bool has_sh = g->shs != nullptr, has_col = g->colors_precomp != nullptr;
+	if (has_sh == has_col && g->P > 0) return fail(RGS_E_INVALID, "Please provide excatly one of either SHs or precomputed colors!");
+	const bool has_sr = g->scales != nullptr && g->rotations != nullptr, has_cov = g->cov3D_precomp != nullptr;
+	if (has_sr == has_cov && g->P > 0)
+		return fail(RGS_E_INVALID, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+	if (has_sh && (cam->sh_degree < 0 || cam->sh_degree > 3 || (cam->sh_degree + 1) * (cam->sh_degree + 1) > cam->sh_coeffs))
+		return fail(RGS_E_INVALID, "sh_degree does not fit the stored SH coefficients");
+	p.P = g->P;
+	p.D = cam->sh_degree;
+	p.M = has_sh ? cam->sh_coeffs : 0;
+	p.W = cam->width;
+	p.H = cam->height;
+	p.grid_x = (cam->width + TILE_X - 1) / TILE_X;
+	p.grid_y = (cam->height + TILE_Y - 1) / TILE_Y;
+	p.row_begin = cam->tile_row_begin;
+	p.row_end = cam->tile_row_end < 0 ? p.grid_y : cam->tile_row_end;
+	if (p.row_begin < 0 || p.row_end > p.grid_y || p.row_begin > p.row_end) return fail(RGS_E_INVALID, "tile row slab out of range");
+	p.tan_fovx = cam->tan_fovx;
+	p.tan_fovy = cam->tan_fovy;
+	// focal lengths computed on the host in float, as the reference does (rasterizer_impl.cu:288-289)
+	p.focal_y = cam->height / (2.0f * cam->tan_fovy);
+	p.focal_x = cam->width / (2.0f * cam->tan_fovx);
+	p.kernel_size = cam->kernel_size;
+	p.scale_modifier = cam->scale_modifier;
+	p.coord = cam->require_coord != 0;
+	p.depth = cam->require_depth != 0;
+	p.means3D = g->means3D;
+	p.opacities = g->opacities;
+	p.shs = g->shs;
+	p.colors_precomp = g->colors_precomp;
+	p.scales = g->scales;
+	p.rotations = g->rotations;
+	p.cov3D_precomp = g->cov3D_precomp;
+	p.viewmatrix = cam->viewmatrix;
+	p.projmatrix = cam->projmatrix;
+	p.cam_pos = cam->cam_pos;
+	p.background = cam->background;
+	return RGS_OK;
+}
+
+// pinned 4-byte mailbox per thread for the num_rendered read-back
+static uint32_t* pinned_mailbox() {
+	static thread_local uint32_t* box = nullptr;
+	if (!box) {
+		if (cudaHostAlloc((void**)&box, 64, cudaHostAllocDefault) != cudaSuccess) box = nullptr;
+	}
+	return box;
+}
+
+}  // namespace rgs
+
+using namespace rgs;
+
+extern "C" {
+
+const char* rgs_last_error(void) { return t_error.c_str(); }
+int32_t rgs_abi_version(void) { return RGS_ABI_VERSION; }
+int64_t rgs_launch_count(void) { return g_launches.load(); }
+int32_t rgs_grad_stride(int32_t require_coord, int32_t /*require_depth*/) { return grad_floats(require_coord != 0); }
+
+int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_forward_out* out, const rgs_buffers* bufs, void* cuda_stream) {
+	FwdParams p;
+	int rc = make_params(cam, gs, p);
+	if (rc != RGS_OK) return rc;
+	if (!out || !bufs || !bufs->geom || !bufs->binning || !bufs->image) return fail(RGS_E_INVALID, "null outputs / buffer callbacks");
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	const int P = p.P;
+	const size_t N = (size_t)p.W * p.H;
+	const int tiles = p.grid_x * p.grid_y;
+
+	// image-side scratch first: needed even when there is nothing to draw (background fill)
+	size_t img_bytes = 0;
+	carve_img(nullptr, tiles, N, p.coord, p.depth, &img_bytes);
+	char* img_ptr = bufs->image(bufs->image_user, img_bytes);
+	if (!img_ptr) return fail(RGS_E_ALLOC, "image buffer callback returned NULL");
+	ImgView img = carve_img(img_ptr, tiles, N, p.coord, p.depth, nullptr);
+	RenderOut ro{out->out_color, out->out_coord, out->out_mcoord, out->out_alpha, out->out_normal, out->out_depth, out->out_mdepth};
+
+	const size_t scan_bytes = P > 0 ? scan_temp_bytes(P) : 0;
+	size_t geom_bytes = 0;
+	carve_geom(nullptr, P, p.coord, scan_bytes, &geom_bytes);
+	char* geom_ptr = bufs->geom(bufs->geom_user, geom_bytes);
+	if (!geom_ptr) return fail(RGS_E_ALLOC, "geometry buffer callback returned NULL");
+	GeomView g = carve_geom(geom_ptr, P, p.coord, scan_bytes, nullptr);
+
+	int64_t R = 0;
+	if (P > 0) {
+		launch_preprocess_forward(p, g, out->radii, s);
+		if ((rc = debug_sync(cam, s, "preprocess")) != RGS_OK) return rc;
+		launch_scan(g, P, s);
+		// the one host sync of the forward pass: instance count sizes the binning buffers and is returned to the
+		// caller (reference: blocking cudaMemcpy, rasterizer_impl.cu:354)
+		uint32_t* box = pinned_mailbox();
+		if (!box) return fail(RGS_E_CUDA, "cudaHostAlloc failed for the num_rendered mailbox");
+		RGS_CUDA_TRY(cudaMemcpyAsync(box, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		RGS_CUDA_TRY(cudaStreamSynchronize(s));
+		R = (int64_t)*box;
+	}
+	const size_t sort_bytes = R > 0 ? sort_temp_bytes((size_t)R) : 0;
+	size_t bin_bytes = 0;
+	carve_bin(nullptr, (size_t)R, sort_bytes, &bin_bytes);
+	char* bin_ptr = bufs->binning(bufs->binning_user, bin_bytes);
+	if (!bin_ptr) return fail(RGS_E_ALLOC, "binning buffer callback returned NULL");
+	BinView b = carve_bin(bin_ptr, (size_t)R, sort_bytes, nullptr);
+
+	launch_binning(p, g, b, img, out->radii, R, s);
+	if ((rc = debug_sync(cam, s, "binning")) != RGS_OK) return rc;
+	launch_render_forward(p, g, b, img, ro, s);
+	if ((rc = debug_sync(cam, s, "render")) != RGS_OK) return rc;
+	return R;
+}
+
+static int backward_views(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, FwdParams& p, GeomView& g, BinView& b, ImgView& img) {
+	int rc = make_params(cam, gs, p);
+	if (rc != RGS_OK) return rc;
+	if (!in || !in->geom_buffer || !in->image_buffer) return fail(RGS_E_INVALID, "null backward inputs / buffers");
+	const size_t N = (size_t)p.W * p.H;
+	const size_t scan_bytes = p.P > 0 ? scan_temp_bytes(p.P) : 0;
+	g = carve_geom(const_cast<char*>(in->geom_buffer), p.P, p.coord, scan_bytes, nullptr);
+	const size_t sort_bytes = in->num_rendered > 0 ? sort_temp_bytes((size_t)in->num_rendered) : 0;
+	b = carve_bin(const_cast<char*>(in->binning_buffer), (size_t)in->num_rendered, sort_bytes, nullptr);
+	img = carve_img(const_cast<char*>(in->image_buffer), p.grid_x * p.grid_y, N, p.coord, p.depth, nullptr);
+	return RGS_OK;
+}
+
+int32_t rgs_backward_render(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, float* grad_accum, void* cuda_stream) {
+	FwdParams p;
+	GeomView g;
+	BinView b;
+	ImgView img;
+	int rc = backward_views(cam, gs, in, p, g, b, img);
+	if (rc != RGS_OK) return rc;
+	if (p.P == 0) return RGS_OK;
+	if (!grad_accum) return fail(RGS_E_INVALID, "null gradient accumulator");
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	RenderGradIn gin{in->dL_dout_color, in->dL_dout_coord, in->dL_dout_mcoord, in->dL_dout_depth, in->dL_dout_mdepth,
+	                 in->dL_dout_alpha, in->dL_dout_normal, in->out_alpha, in->out_normal};
+	launch_render_backward(p, g, b, img, gin, grad_accum, s);
+	return debug_sync(cam, s, "backward render");
+}
+
+int32_t rgs_backward_preprocess(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, const float* grad_accum,
+                                const rgs_backward_out* out, void* cuda_stream) {
+	FwdParams p;
+	GeomView g;
+	BinView b;
+	ImgView img;
+	int rc = backward_views(cam, gs, in, p, g, b, img);
+	if (rc != RGS_OK) return rc;
+	if (p.P == 0) return RGS_OK;
+	if (!grad_accum || !out) return fail(RGS_E_INVALID, "null gradient accumulator / outputs");
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	ParamGradOut po{out->dL_dmeans2D, out->dL_dcolors, out->dL_dopacity, out->dL_dmeans3D, out->dL_dcov3D, out->dL_dsh, out->dL_dscales, out->dL_drotations};
+	launch_preprocess_backward(p, g, in->radii, grad_accum, po, s);
+	return debug_sync(cam, s, "backward preprocess");
+}
+
+int32_t rgs_backward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, const rgs_backward_out* out,
+                     rgs_resize_fn grad_scratch, void* grad_scratch_user, void* cuda_stream) {
+	if (!gs || !cam) return fail(RGS_E_INVALID, "null camera / gaussians");
+	if (gs->P == 0) return RGS_OK;
+	if (!grad_scratch) return fail(RGS_E_INVALID, "null scratch callback");
+	const size_t bytes = (size_t)gs->P * grad_floats(cam->require_coord != 0) * sizeof(float);
+	float* acc = reinterpret_cast<float*>(grad_scratch(grad_scratch_user, bytes));
+	if (!acc) return fail(RGS_E_ALLOC, "gradient scratch callback returned NULL");
+	int rc = rgs_backward_render(cam, gs, in, acc, cuda_stream);
+	if (rc != RGS_OK) return rc;
+	return rgs_backward_preprocess(cam, gs, in, acc, out, cuda_stream);
+}
+
+int32_t rgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* /*projmatrix*/, uint8_t* present, void* cuda_stream) {
+	if (P < 0) return fail(RGS_E_INVALID, "negative Gaussian count");
+	if (P == 0) return RGS_OK;
+	if (!means3D || !viewmatrix || !present) return fail(RGS_E_INVALID, "null pointer");
+	launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)cuda_stream);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(RGS_E_CUDA, cudaGetErrorString(e));
+	return RGS_OK;
+}
+
+int32_t rgs_debug_get_views(const rgs_camera* cam, int32_t P, int64_t num_rendered, const char* geom_buffer, const char* binning_buffer,
+                            const char* image_buffer, rgs_debug_views* views) {
+	if (!cam || !views) return fail(RGS_E_INVALID, "null pointer");
+	const bool coord = cam->require_coord != 0, depth = cam->require_depth != 0;
+	const int grid_x = (cam->width + TILE_X - 1) / TILE_X, grid_y = (cam->height + TILE_Y - 1) / TILE_Y;
+	const size_t N = (size_t)cam->width * cam->height;
+	const size_t scan_bytes = P > 0 ? scan_temp_bytes(P) : 0;
+	GeomView g = carve_geom(const_cast<char*>(geom_buffer), P, coord, scan_bytes, nullptr);
+	const size_t sort_bytes = num_rendered > 0 ? sort_temp_bytes((size_t)num_rendered) : 0;
+	BinView b = carve_bin(const_cast<char*>(binning_buffer), (size_t)num_rendered, sort_bytes, nullptr);
+	ImgView img = carve_img(const_cast<char*>(image_buffer), grid_x * grid_y, N, coord, depth, nullptr);
+	views->point_list = b.point_list;
+	views->point_list_keys = b.keys_sorted;
+	views->tile_ranges = reinterpret_cast<const uint32_t*>(img.ranges);
+	views->n_contrib = img.n_contrib;
+	views->tiles_touched = g.tiles_touched;
+	views->records = g.records;
+	views->record_floats = rec_floats(coord);
+	views->depths = g.depths;
+	return RGS_OK;
+}
+
+}  // extern "C"

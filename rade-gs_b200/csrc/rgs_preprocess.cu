@@ -1,0 +1,248 @@
+// rgs_preprocess.cu -- per-Gaussian forward preprocess for sm_100a.
+//
+// Replaces preprocessCUDA<3,false> + computeCov3D + computeCov2D<false> + computeColorFromSH
+// (reference: cuda_rasterizer/forward.cu:23-74, 77-264, 270-304, 307-423) and checkFrustum
+// (cuda_rasterizer/rasterizer_impl.cu:54-66).
+//
+// What is different from the reference (by design, results within tolerance; keys bit-exact):
+//   * one packed 64/96-byte render record per Gaussian instead of nine SoA arrays;
+//   * the 3x3 symmetric eigen-decomposition of Sigma (forward.cu:135-155) is not iterated when Sigma
+//     comes from (scale, unit quaternion): Sigma = R S^2 R^T already IS its eigen-decomposition, so
+//     Sigma^-1 in camera space is A diag(1/s^2) A^T with A = R_view * R.  A Jacobi solver covers
+//     cov3D_precomp and non-unit quaternions;
+//   * the key-determining chain (p_view.z, NDC->pixel, cov2D -> radius -> tile rect) keeps the
+//     reference's expression shapes so both builds round identically.
+#include <math_constants.h>
+
+#include "rgs_geom.cuh"
+
+namespace rgs {
+
+// SH -> RGB (forward.cu:23-74).  `sh` points at this Gaussian's [M,3] block.
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ sh, float3 pos, float3 campos, uint8_t& clamp_bits) {
+	float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
+	float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+	dir.x /= len; dir.y /= len; dir.z /= len;
+
+	float c[48];
+	const int ncoef = (deg + 1) * (deg + 1);
+	if ((reinterpret_cast<uintptr_t>(sh) & 15) == 0) {
+		const float4* s4 = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+		for (int i = 0; i < 12; i++) {
+			if (i * 4 < ncoef * 3) {
+				float4 v = __ldg(s4 + i);
+				c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
+			}
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < 48; i++)
+			if (i < ncoef * 3) c[i] = __ldg(sh + i);
+	}
+#define SH(k, ch) c[3 * (k) + (ch)]
+	float res[3];
+	const float x = dir.x, y = dir.y, z = dir.z;
+#pragma unroll
+	for (int ch = 0; ch < 3; ch++) {
+		float r = kSH0 * SH(0, ch);
+		if (deg > 0) {
+			r = r - kSH1 * y * SH(1, ch) + kSH1 * z * SH(2, ch) - kSH1 * x * SH(3, ch);
+			if (deg > 1) {
+				float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+				r = r + kSH2[0] * xy * SH(4, ch) + kSH2[1] * yz * SH(5, ch) + kSH2[2] * (2.0f * zz - xx - yy) * SH(6, ch) +
+				    kSH2[3] * xz * SH(7, ch) + kSH2[4] * (xx - yy) * SH(8, ch);
+				if (deg > 2) {
+					r = r + kSH3[0] * y * (3.0f * xx - yy) * SH(9, ch) + kSH3[1] * xy * z * SH(10, ch) +
+					    kSH3[2] * y * (4.0f * zz - xx - yy) * SH(11, ch) + kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SH(12, ch) +
+					    kSH3[4] * x * (4.0f * zz - xx - yy) * SH(13, ch) + kSH3[5] * z * (xx - yy) * SH(14, ch) +
+					    kSH3[6] * x * (xx - 3.0f * yy) * SH(15, ch);
+				}
+			}
+		}
+		res[ch] = r + 0.5f;
+	}
+#undef SH
+	clamp_bits = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
+	return float3{fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f)};
+}
+
+__global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, GeomView g, int* __restrict__ radii) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= p.P) return;
+
+	// Not rendered unless proven otherwise (forward.cu:346-349).
+	int my_radii = 0;
+	uint32_t my_tiles = 0;
+
+	const float* V = p.viewmatrix;
+	const float3 p_orig = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
+	const float3 p_view = xform4x3(p_orig, V);
+
+	// near-plane cull only (auxiliary.h:170)
+	if (p_view.z > 0.2f) {
+		const float4 p_hom = xform4x4(p_orig, p.projmatrix);
+		const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+		const float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+
+		// ---- 3D covariance (forward.cu:270-304) ----
+		float cov3D[6];
+		M3 Rg;
+		V3 s_mod = {0.f, 0.f, 0.f};
+		bool analytic = false;
+		if (p.cov3D_precomp != nullptr) {
+#pragma unroll
+			for (int i = 0; i < 6; i++) cov3D[i] = p.cov3D_precomp[6 * idx + i];
+			Rg = m3(1, 0, 0, 0, 1, 0, 0, 0, 1);
+		} else {
+			const float sx = p.scales[3 * idx], sy = p.scales[3 * idx + 1], sz = p.scales[3 * idx + 2];
+			const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * idx);
+			s_mod = V3{p.scale_modifier * sx, p.scale_modifier * sy, p.scale_modifier * sz};
+			M3 S = m3(s_mod.x, 0.f, 0.f, 0.f, s_mod.y, 0.f, 0.f, 0.f, s_mod.z);
+			Rg = quat_to_glm_rot(q.x, q.y, q.z, q.w);
+			M3 Mm = S * Rg;
+			M3 Sigma = transpose(Mm) * Mm;
+			cov3D[0] = Sigma.c[0].x; cov3D[1] = Sigma.c[0].y; cov3D[2] = Sigma.c[0].z;
+			cov3D[3] = Sigma.c[1].y; cov3D[4] = Sigma.c[1].z; cov3D[5] = Sigma.c[2].z;
+			const float qn = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+			analytic = fabsf(qn - 1.0f) < 1e-4f;
+		}
+
+		// ---- EWA 2D covariance (forward.cu:85-124); this chain decides the radius ----
+		float3 t = p_view;
+		const float limx = 1.3f * p.tan_fovx;
+		const float limy = 1.3f * p.tan_fovy;
+		float txtz = t.x / t.z;
+		float tytz = t.y / t.z;
+		t.x = min(limx, max(-limx, txtz)) * t.z;
+		t.y = min(limy, max(-limy, tytz)) * t.z;
+		txtz = t.x / t.z;
+		tytz = t.y / t.z;
+
+		M3 J = m3(p.focal_x / t.z, 0.0f, -(p.focal_x * t.x) / (t.z * t.z),
+		          0.0f, p.focal_y / t.z, -(p.focal_y * t.y) / (t.z * t.z),
+		          0.f, 0.f, 0.f);
+		M3 Wm = m3(V[0], V[4], V[8], V[1], V[5], V[9], V[2], V[6], V[10]);
+		M3 T = Wm * J;
+		M3 Vrk = m3(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+		M3 cov = transpose(T) * transpose(Vrk) * T;
+
+		const float c00 = cov.c[0].x, c01 = cov.c[0].y, c11 = cov.c[1].y;
+		const float3 cov2 = {float(c00 + p.kernel_size), float(c01), float(c11 + p.kernel_size)};
+		const float det_0 = max(1e-6, c00 * c11 - c01 * c01);
+		const float det_1 = max(1e-6, (c00 + p.kernel_size) * (c11 + p.kernel_size) - c01 * c01);
+		float coef = sqrt(det_0 / (det_1 + 1e-6) + 1e-6);
+		if (det_0 <= 1e-6 || det_1 <= 1e-6) coef = 0.0f;
+
+		// Invert covariance (forward.cu:385-389)
+		const float det = (cov2.x * cov2.z - cov2.y * cov2.y);
+		if (det != 0.0f) {
+			const float det_inv = 1.f / det;
+			const float3 conic = {cov2.z * det_inv, -cov2.y * det_inv, cov2.x * det_inv};
+
+			// extent -> tile rectangle (forward.cu:395-403)
+			const float mid = 0.5f * (cov2.x + cov2.z);
+			const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+			const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+			const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+			const float2 point_image = {ndc_to_pix(p_proj.x, p.W), ndc_to_pix(p_proj.y, p.H)};
+			uint2 rect_min, rect_max;
+			tile_rect(point_image, my_radius, p.grid_x, p.grid_y, rect_min, rect_max);
+			if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) != 0) {
+				// ---- geometry terms: ray-space plane, camera-space plane, normal (forward.cu:135-262) ----
+				float cam_plane[6] = {0, 0, 0, 0, 0, 0};
+				float2 ray_plane = {0.f, 0.f};
+				float3 normal = {0.f, 0.f, 0.f};
+				if (p.coord || p.depth) {
+					float lam[3];
+					M3 E;
+					sigma_eigen(analytic, Rg, s_mod, cov3D, lam, E);
+					bool well;
+					int min_id;
+					const V3 uvh = {txtz, tytz, 1.f};
+					const V3 uvh_m = apply_cov_cam_inv(E, lam, V, uvh, well, min_id);
+					const float inv_len = 1.0f / sqrtf(dot3(uvh_m, uvh_m));
+					const V3 uvh_mn = uvh_m * inv_len;
+					if (!isnan(uvh_mn.x)) {
+						const float u2 = txtz * txtz, v2 = tytz * tytz, uv = txtz * tytz;
+						const float l = sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+						const float vbn = dot3(uvh_mn, uvh);
+						const float nl = u2 + v2 + 1;
+						const float factor_normal = l / nl;
+						const V3 q = uvh_mn / max(vbn, 0.0000001f);
+						const float plane0 = (v2 + 1) * q.x + (-uv) * q.y + (-txtz) * q.z;
+						const float plane1 = (-uv) * q.x + (u2 + 1) * q.y + (-tytz) * q.z;
+						cam_plane[0] = (-(v2 + 1) * t.z + plane0 * t.x) / nl / p.focal_x;
+						cam_plane[1] = (uv * t.z + plane1 * t.x) / nl / p.focal_y;
+						cam_plane[2] = (uv * t.z + plane0 * t.y) / nl / p.focal_x;
+						cam_plane[3] = (-(u2 + 1) * t.z + plane1 * t.y) / nl / p.focal_y;
+						cam_plane[4] = (t.x + plane0 * t.z) / nl / p.focal_x;
+						cam_plane[5] = (t.y + plane1 * t.z) / nl / p.focal_y;
+						ray_plane = {plane0 * l / nl / p.focal_x, plane1 * l / nl / p.focal_y};
+						const V3 rn = {-plane0 * factor_normal, -plane1 * factor_normal, -1.f};
+						const V3 cn = {rn.x / t.z + rn.z * (t.x / l), rn.y / t.z + rn.z * (t.y / l),
+						               (-(t.x) / (t.z * t.z)) * rn.x + (-(t.y) / (t.z * t.z)) * rn.y + (t.z / l) * rn.z};
+						const float cinv = 1.0f / sqrtf(dot3(cn, cn));
+						normal = {cn.x * cinv, cn.y * cinv, cn.z * cinv};
+					}
+				}
+
+				// ---- colour (forward.cu:405-413) ----
+				float3 rgb;
+				uint8_t clamp_bits = 0;
+				if (p.colors_precomp == nullptr) {
+					const float3 campos = {p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]};
+					rgb = sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, p_orig, campos, clamp_bits);
+				} else {
+					rgb = {p.colors_precomp[3 * idx], p.colors_precomp[3 * idx + 1], p.colors_precomp[3 * idx + 2]};
+				}
+				g.clamped[idx] = clamp_bits;
+
+				const float ts = sqrt(p_view.x * p_view.x + p_view.y * p_view.y + p_view.z * p_view.z);
+				const float opac = p.opacities[idx] * coef;
+
+				// ---- packed record ----
+				const int RF = rec_floats(p.coord);
+				float4* rec = reinterpret_cast<float4*>(g.records + (size_t)idx * RF);
+				rec[0] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+				rec[1] = make_float4(conic.z, opac, ts, ray_plane.x);
+				rec[2] = make_float4(ray_plane.y, rgb.x, rgb.y, rgb.z);
+				rec[3] = make_float4(normal.x, normal.y, normal.z, cam_plane[5]);
+				if (p.coord) {
+					rec[4] = make_float4(p_view.x, p_view.y, p_view.z, cam_plane[0]);
+					rec[5] = make_float4(cam_plane[1], cam_plane[2], cam_plane[3], cam_plane[4]);
+				}
+				g.depths[idx] = p_view.z;
+				my_radii = (int)my_radius;
+				// tiles of THIS call's slab of tile rows (whole image on a single GPU)
+				const int ry0 = max((int)rect_min.y, p.row_begin);
+				const int ry1 = min((int)rect_max.y, p.row_end);
+				my_tiles = (rect_max.x - rect_min.x) * (uint32_t)max(0, ry1 - ry0);
+			}
+		}
+	}
+	radii[idx] = my_radii;
+	g.tiles_touched[idx] = my_tiles;
+}
+
+void launch_preprocess_forward(const FwdParams& p, GeomView g, int* radii, cudaStream_t s) {
+	const int threads = 256;
+	const int blocks = (p.P + threads - 1) / threads;
+	preprocess_forward_kernel<<<blocks, threads, 0, s>>>(p, g, radii);
+	count_launch();
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ V, uint8_t* __restrict__ present) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P) return;
+	const float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+	const float3 p_view = xform4x3(p_orig, V);
+	present[idx] = p_view.z > 0.2f ? 1 : 0;
+}
+
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s) {
+	mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
+	count_launch();
+}
+
+}  // namespace rgs

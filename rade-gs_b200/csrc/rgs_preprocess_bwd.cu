@@ -1,0 +1,451 @@
+// rgs_preprocess_bwd.cu -- per-Gaussian backward preprocess for sm_100a.
+//
+// Replaces, fused into one kernel, computeCov2DCUDA + preprocessCUDA<3> backward with
+// computeColorFromSH / computeCov3D backward (reference: cuda_rasterizer/backward.cu:145-488, 560-628,
+// 21-140, 492-555).  Input is the packed screen-space gradient row written by backward-render; output
+// is every parameter gradient the API returns, fully written (zeros for Gaussians that were not rendered),
+// so the host allocates with empty() instead of fourteen zero-fills (rasterize_points.cu:180-193).
+//
+// Faithfulness notes:
+//   * the hand-derived, epsilon-regularised gradient of the mip coefficient is restated as is, INCLUDING the
+//     reference's aliasing bug: BACKWARD::preprocess receives dL_dconic where conic_opacity is expected
+//     (rasterizer_impl.cu:569 vs backward.h:94), so `combined_opacity` below is dL_dconic.w.  Set
+//     RGS_FIX_MIP_GRADIENT to use the true opacity*coef instead (off by default: parity first);
+//   * gradients are w.r.t. the quaternion as given (no normalisation inside, backward.cu:554);
+//   * Sigma's eigen-decomposition is analytic for (scale, unit quaternion) inputs, Jacobi otherwise
+//     (see rgs_preprocess.cu).
+#include "rgs_geom.cuh"
+
+namespace rgs {
+
+namespace {
+
+// y = Sigma^-1-like operator in WORLD space applied to x: E diag(1/lam) E^T x, or e_min (e_min . x).
+__device__ __forceinline__ V3 apply_world_inv(const M3& E, const float lam[3], bool well, int min_id, V3 x) {
+	if (well) {
+		const float w0 = dot3(E.c[0], x) / lam[0], w1 = dot3(E.c[1], x) / lam[1], w2 = dot3(E.c[2], x) / lam[2];
+		return V3{E.c[0].x * w0 + E.c[1].x * w1 + E.c[2].x * w2, E.c[0].y * w0 + E.c[1].y * w1 + E.c[2].y * w2,
+		          E.c[0].z * w0 + E.c[1].z * w1 + E.c[2].z * w2};
+	}
+	const V3 e = min_id == 0 ? E.c[0] : (min_id == 1 ? E.c[1] : E.c[2]);
+	return e * dot3(e, x);
+}
+// Rv * x  and  Rv^T * x  for the rotation part of the view matrix (Rv[i][j] = V[i + 4 j])
+__device__ __forceinline__ V3 rot_view(const float* V, V3 x) {
+	return V3{V[0] * x.x + V[4] * x.y + V[8] * x.z, V[1] * x.x + V[5] * x.y + V[9] * x.z, V[2] * x.x + V[6] * x.y + V[10] * x.z};
+}
+__device__ __forceinline__ V3 rot_view_T(const float* V, V3 x) {
+	return V3{V[0] * x.x + V[1] * x.y + V[2] * x.z, V[4] * x.x + V[5] * x.y + V[6] * x.z, V[8] * x.x + V[9] * x.y + V[10] * x.z};
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, GeomView g, const int* __restrict__ radii,
+                                                                   const float* __restrict__ grad_accum, ParamGradOut out, int fix_mip) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= p.P) return;
+	const int M = p.M;
+	const bool visible = radii[idx] > 0;
+
+	float o_means2D[3] = {0, 0, 0}, o_colors[3] = {0, 0, 0}, o_opacity = 0.f, o_mean3D[3] = {0, 0, 0};
+	float o_cov[6] = {0, 0, 0, 0, 0, 0}, o_scale[3] = {0, 0, 0}, o_rot[4] = {0, 0, 0, 0};
+
+	if (!visible) {
+		if (out.d_sh != nullptr) {
+			float* dsh = out.d_sh + (size_t)idx * M * 3;
+			for (int i = 0; i < 3 * M; i++) dsh[i] = 0.f;
+		}
+	} else {
+		const int GF = grad_floats(p.coord);
+		const float* ga = grad_accum + (size_t)idx * GF;
+		float gr[GRAD_FLOATS_COORD];
+#pragma unroll
+		for (int i = 0; i < GRAD_FLOATS_BASE / 4; i++) {
+			const float4 v = *reinterpret_cast<const float4*>(ga + 4 * i);
+			gr[4 * i] = v.x; gr[4 * i + 1] = v.y; gr[4 * i + 2] = v.z; gr[4 * i + 3] = v.w;
+		}
+		if (p.coord) {
+#pragma unroll
+			for (int i = GRAD_FLOATS_BASE / 4; i < GRAD_FLOATS_COORD / 4; i++) {
+				const float4 v = *reinterpret_cast<const float4*>(ga + 4 * i);
+				gr[4 * i] = v.x; gr[4 * i + 1] = v.y; gr[4 * i + 2] = v.z; gr[4 * i + 3] = v.w;
+			}
+		} else {
+#pragma unroll
+			for (int i = GRAD_FLOATS_BASE; i < GRAD_FLOATS_COORD; i++) gr[i] = 0.f;
+		}
+
+		const float* V = p.viewmatrix;
+		const float h_x = p.focal_x, h_y = p.focal_y;
+		const float ddelx_dx = 0.5 * p.W, ddely_dy = 0.5 * p.H;
+
+		// ---- gradients handed over by backward-render, constant factors applied here ----
+		const float3 dL_dconic = {gr[G_CONX], gr[G_CONY], gr[G_CONW]};
+		const V3 dL_dnormal = {gr[G_NRM], gr[G_NRM + 1], gr[G_NRM + 2]};
+		const float2 dcp0 = {gr[G_CP + 0] / h_x, gr[G_CP + 1] / h_y};
+		const float2 dcp1 = {gr[G_CP + 2] / h_x, gr[G_CP + 3] / h_y};
+		const float2 dcp2 = {gr[G_CP + 4] / h_x, gr[G_CP + 5] / h_y};
+		const float2 dray = {gr[G_RAYX] / h_x, gr[G_RAYY] / h_y};
+		const float dL_dts = gr[G_T];
+		const float3 dL_dview_point = {gr[G_VP], gr[G_VP + 1], gr[G_VP + 2]};
+		const float2 dL_dmean2D = {gr[G_MX] * ddelx_dx, gr[G_MY] * ddely_dy};
+		float dL_dopacity = gr[G_OPA];
+		o_means2D[0] = dL_dmean2D.x; o_means2D[1] = dL_dmean2D.y; o_means2D[2] = gr[G_MABS];
+		o_colors[0] = gr[G_COL]; o_colors[1] = gr[G_COL + 1]; o_colors[2] = gr[G_COL + 2];
+
+		// ---- recompute forward intermediates (backward.cu:166-252) ----
+		const float3 mean = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
+		float cov3D[6];
+		M3 Rg = m3(1, 0, 0, 0, 1, 0, 0, 0, 1);
+		V3 s_mod = {0, 0, 0};
+		float4 q = {1, 0, 0, 0};
+		bool analytic = false;
+		const bool from_scales = (p.cov3D_precomp == nullptr);
+		if (!from_scales) {
+#pragma unroll
+			for (int i = 0; i < 6; i++) cov3D[i] = p.cov3D_precomp[6 * idx + i];
+		} else {
+			q = *reinterpret_cast<const float4*>(p.rotations + 4 * idx);
+			s_mod = V3{p.scale_modifier * p.scales[3 * idx], p.scale_modifier * p.scales[3 * idx + 1], p.scale_modifier * p.scales[3 * idx + 2]};
+			M3 S = m3(s_mod.x, 0.f, 0.f, 0.f, s_mod.y, 0.f, 0.f, 0.f, s_mod.z);
+			Rg = quat_to_glm_rot(q.x, q.y, q.z, q.w);
+			M3 Mm = S * Rg;
+			M3 Sigma = transpose(Mm) * Mm;
+			cov3D[0] = Sigma.c[0].x; cov3D[1] = Sigma.c[0].y; cov3D[2] = Sigma.c[0].z;
+			cov3D[3] = Sigma.c[1].y; cov3D[4] = Sigma.c[1].z; cov3D[5] = Sigma.c[2].z;
+			const float qn = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+			analytic = fabsf(qn - 1.0f) < 1e-4f;
+		}
+
+		float3 t = xform4x3(mean, V);
+		const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
+		float txtz = t.x / t.z, tytz = t.y / t.z;
+		t.x = min(limx, max(-limx, txtz)) * t.z;
+		t.y = min(limy, max(-limy, tytz)) * t.z;
+		const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
+		const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
+		txtz = t.x / t.z;
+		tytz = t.y / t.z;
+
+		M3 J = m3(h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z), 0.0f, h_y / t.z, -(h_y * t.y) / (t.z * t.z), 0.f, 0.f, 0.f);
+		M3 Wm = m3(V[0], V[4], V[8], V[1], V[5], V[9], V[2], V[6], V[10]);
+		M3 Vrk = m3(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+		M3 T = Wm * J;
+		M3 cov2D = transpose(T) * transpose(Vrk) * T;
+		const float c00 = cov2D.c[0].x, c01 = cov2D.c[0].y, c11 = cov2D.c[1].y;
+		const float ks = p.kernel_size;
+		const float det_0 = max(1e-6, c00 * c11 - c01 * c01);
+		const float det_1 = max(1e-6, (c00 + ks) * (c11 + ks) - c01 * c01);
+		const float coef = sqrt(det_0 / (det_1 + 1e-6) + 1e-6);
+
+		// ---- geometry backward: planes / normal -> Sigma, t (backward.cu:221-365) ----
+		const float u2 = txtz * txtz, v2 = tytz * tytz, uv = txtz * tytz;
+		float dVrk[6] = {0, 0, 0, 0, 0, 0};  // symmetric-summed: xx, xy+yx, xz+zx, yy, yz+zy, zz
+		float plane0 = 0.f, plane1 = 0.f, dL_du = 0.f, dL_dv = 0.f, dL_dl = 0.f, l = 1.f, nl = 1.f;
+		V3 dcn = {0, 0, 0}, rn = {0, 0, 0};  // dL_dnJ = dcn * rn^T
+		if (p.coord || p.depth) {
+			float lam[3];
+			M3 E;
+			if (analytic) {
+				lam[0] = s_mod.x * s_mod.x; lam[1] = s_mod.y * s_mod.y; lam[2] = s_mod.z * s_mod.z;
+				E = transpose(Rg);
+			} else {
+				eig_sym3_jacobi(cov3D, lam, E);
+			}
+			const int min_id = lam[0] > lam[1] ? (lam[1] > lam[2] ? 2 : 1) : (lam[0] > lam[2] ? 2 : 0);
+			const bool well = lam[min_id] > 0.00000001f;
+			const V3 uvh = {txtz, tytz, 1.f};
+			const V3 W_uvh = rot_view_T(V, uvh);                                   // W * uvh (world)
+			const V3 uvh_m = rot_view(V, apply_world_inv(E, lam, well, min_id, W_uvh));  // cov_cam_inv * uvh
+			const V3 uvh_mn = uvh_m * (1.0f / sqrtf(dot3(uvh_m, uvh_m)));
+			if (!isnan(uvh_mn.x)) {
+				const float vb = dot3(uvh_m, uvh);
+				const float vbn = dot3(uvh_mn, uvh);
+				l = sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+				const float clamp_vb = max(vb, 0.0000001f);
+				const float clamp_vbn = max(vbn, 0.0000001f);
+				nl = u2 + v2 + 1;
+				const float factor_normal = l / nl;
+				const V3 qv = uvh_mn / clamp_vbn;  // uvh_m_vb
+				plane0 = (v2 + 1) * qv.x + (-uv) * qv.y + (-txtz) * qv.z;
+				plane1 = (-uv) * qv.x + (u2 + 1) * qv.y + (-tytz) * qv.z;
+				const float2 cp0 = {(-(v2 + 1) * t.z + plane0 * t.x) / nl, (uv * t.z + plane1 * t.x) / nl};
+				const float2 cp1 = {(uv * t.z + plane0 * t.y) / nl, (-(u2 + 1) * t.z + plane1 * t.y) / nl};
+				const float2 cp2 = {(t.x + plane0 * t.z) / nl, (t.y + plane1 * t.z) / nl};
+				const float2 ray_plane = {plane0 * factor_normal, plane1 * factor_normal};
+				rn = V3{-plane0 * factor_normal, -plane1 * factor_normal, -1.f};
+				// nJ rows: (1/tz, 0, tx/l), (0, 1/tz, ty/l), (-tx/tz^2, -ty/tz^2, tz/l)
+				const V3 cn = {rn.x / t.z + rn.z * (t.x / l), rn.y / t.z + rn.z * (t.y / l),
+				               (-(t.x) / (t.z * t.z)) * rn.x + (-(t.y) / (t.z * t.z)) * rn.y + (t.z / l) * rn.z};
+				const float lv = sqrtf(dot3(cn, cn));
+				const V3 nvec = cn * (1.0f / lv);
+				const V3 dn_lv = dL_dnormal / lv;
+				dcn = dn_lv - nvec * dot3(nvec, dn_lv);
+				// transpose(nJ) * dcn
+				const V3 drn = {dcn.x / t.z + (-(t.x) / (t.z * t.z)) * dcn.z, dcn.y / t.z + (-(t.y) / (t.z * t.z)) * dcn.z,
+				                (t.x / l) * dcn.x + (t.y / l) * dcn.y + (t.z / l) * dcn.z};
+				dL_dl = (-plane0 * drn.x - plane1 * drn.y + plane0 * dray.x + plane1 * dray.y) / nl;
+				const float dpx = (t.x * dcp0.x + t.y * dcp1.x + t.z * dcp2.x - l * drn.x + dray.x * l) / nl;
+				const float dpy = (t.x * dcp0.y + t.y * dcp1.y + t.z * dcp2.y - l * drn.y + dray.y * l) / nl;
+				const float dL_dnl = (-dcp0.x * cp0.x - dcp0.y * cp0.y - dcp1.x * cp1.x - dcp1.y * cp1.y - dcp2.x * cp2.x - dcp2.y * cp2.y -
+				                      drn.x * rn.x - drn.y * rn.y - dray.x * ray_plane.x - dray.y * ray_plane.y) / nl;
+				const float tmp = dpx * plane0 + dpy * plane1;
+				// transpose(nJ_inv) * (dpx, dpy, 0)
+				const V3 njt_dp = {(v2 + 1) * dpx + (-uv) * dpy, (-uv) * dpx + (u2 + 1) * dpy, (-txtz) * dpx + (-tytz) * dpy};
+				const V3 W_njt = rot_view_T(V, njt_dp);
+				if (well) {
+					// dL_dVrk = -(Sinv w)(Sinv/vb (w*(-tmp) + W njt))^T
+					const V3 a = apply_world_inv(E, lam, true, min_id, W_uvh);
+					const V3 rhs = W_uvh * (-tmp) + W_njt;
+					const V3 b = apply_world_inv(E, lam, true, min_id, rhs) / clamp_vb;
+					dVrk[0] = -(a.x * b.x);
+					dVrk[3] = -(a.y * b.y);
+					dVrk[5] = -(a.z * b.z);
+					dVrk[1] = -(a.x * b.y) - (a.y * b.x);
+					dVrk[2] = -(a.x * b.z) - (a.z * b.x);
+					dVrk[4] = -(a.y * b.z) - (a.z * b.y);
+				} else {
+					const float dL_dvb = -tmp / clamp_vb;
+					const V3 c = W_uvh * dL_dvb + rot_view_T(V, njt_dp / clamp_vb);
+					const V3 emin = min_id == 0 ? E.c[0] : (min_id == 1 ? E.c[1] : E.c[2]);
+					// (w c^T + c w^T) e_min
+					const V3 dLdv = W_uvh * dot3(c, emin) + c * dot3(W_uvh, emin);
+#pragma unroll
+					for (int j = 0; j < 3; j++) {
+						if (j != min_id) {
+							const V3 ej = E.c[j];
+							const float scale = dot3(ej, dLdv) / min(lam[min_id] - lam[j], -0.0000001f);
+							const V3 a = ej * scale;  // outer(a, emin)
+							dVrk[0] += a.x * emin.x;
+							dVrk[3] += a.y * emin.y;
+							dVrk[5] += a.z * emin.z;
+							dVrk[1] += a.x * emin.y + a.y * emin.x;
+							dVrk[2] += a.x * emin.z + a.z * emin.x;
+							dVrk[4] += a.y * emin.z + a.z * emin.y;
+						}
+					}
+				}
+				// dL_duvh = 2(-tmp) q + cov_cam_inv/vb * njt_dp
+				const V3 cci = rot_view(V, apply_world_inv(E, lam, well, min_id, W_njt)) / clamp_vb;
+				const V3 dL_duvh = qv * (2 * (-tmp)) + cci;
+				// dL_dnJ_inv = (dpx,dpy,0) q^T
+				const float nji01 = dpy * qv.x, nji10 = dpx * qv.y, nji11 = dpy * qv.y, nji00 = dpx * qv.x, nji20 = dpx * qv.z, nji21 = dpy * qv.z;
+				dL_du = dL_dnl * 2 * txtz + dL_duvh.x + (nji01 + nji10) * (-tytz) + 2 * nji11 * txtz - nji20 +
+				        (dcp0.y * t.y + dcp1.x * t.y + dcp1.y * (-2 * t.x)) / nl;
+				dL_dv = dL_dnl * 2 * tytz + dL_duvh.y + (nji01 + nji10) * (-txtz) + 2 * nji00 * tytz - nji21 +
+				        (dcp0.x * (-2 * t.y) + dcp0.y * t.x + dcp1.x * t.x) / nl;
+			} else {
+				dcn = V3{0, 0, 0};
+				rn = V3{0, 0, 0};
+			}
+		}
+
+		// ---- mip-coefficient and conic backward (backward.cu:367-431) ----
+		// fixed mode reads the true opacity*coef that forward stored in the render record (slot 5)
+		const float combined_opacity = fix_mip ? g.records[(size_t)idx * rec_floats(p.coord) + 5] : dL_dconic.z;
+		const float opacity = combined_opacity / (coef + 1e-6);
+		const float dL_dcoef = dL_dopacity * opacity;
+		const float dL_dsqrtcoef = dL_dcoef * 0.5 * 1. / (coef + 1e-6);
+		const float dL_ddet0 = dL_dsqrtcoef / (det_1 + 1e-6);
+		const float dL_ddet1 = dL_dsqrtcoef * det_0 * (-1.f / (det_1 * det_1 + 1e-6));
+		const float dcoef_da = dL_ddet0 * c11 + dL_ddet1 * (c11 + ks);
+		const float dcoef_db = dL_ddet0 * (-2. * c01) + dL_ddet1 * (-2. * c01);
+		const float dcoef_dc = dL_ddet0 * c00 + dL_ddet1 * (c00 + ks);
+		const float a = c00 + ks, b = c01, c = c11 + ks;
+		const float denom = a * c - b * b;
+		float dL_da = 0, dL_db = 0, dL_dc = 0;
+		const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+#define TT(col, row) at(T, col, row)
+#define VV(col, row) at(Vrk, col, row)
+		if (denom2inv != 0) {
+			dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
+			dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
+			dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
+			if (det_0 <= 1e-6 || det_1 <= 1e-6) {
+				dL_dopacity = 0;
+			} else {
+				dL_da += dcoef_da;
+				dL_dc += dcoef_dc;
+				dL_db += dcoef_db;
+				dL_dopacity = dL_dopacity * coef;
+			}
+			o_cov[0] = (TT(0, 0) * TT(0, 0) * dL_da + TT(0, 0) * TT(1, 0) * dL_db + TT(1, 0) * TT(1, 0) * dL_dc);
+			o_cov[3] = (TT(0, 1) * TT(0, 1) * dL_da + TT(0, 1) * TT(1, 1) * dL_db + TT(1, 1) * TT(1, 1) * dL_dc);
+			o_cov[5] = (TT(0, 2) * TT(0, 2) * dL_da + TT(0, 2) * TT(1, 2) * dL_db + TT(1, 2) * TT(1, 2) * dL_dc);
+			o_cov[1] = 2 * TT(0, 0) * TT(0, 1) * dL_da + (TT(0, 0) * TT(1, 1) + TT(0, 1) * TT(1, 0)) * dL_db + 2 * TT(1, 0) * TT(1, 1) * dL_dc;
+			o_cov[2] = 2 * TT(0, 0) * TT(0, 2) * dL_da + (TT(0, 0) * TT(1, 2) + TT(0, 2) * TT(1, 0)) * dL_db + 2 * TT(1, 0) * TT(1, 2) * dL_dc;
+			o_cov[4] = 2 * TT(0, 2) * TT(0, 1) * dL_da + (TT(0, 1) * TT(1, 2) + TT(0, 2) * TT(1, 1)) * dL_db + 2 * TT(1, 1) * TT(1, 2) * dL_dc;
+		}
+#pragma unroll
+		for (int i = 0; i < 6; i++) o_cov[i] += dVrk[i];
+		o_opacity = dL_dopacity;
+
+		// ---- T -> J -> t (backward.cu:433-477) ----
+		const float dL_dT00 = 2 * (TT(0, 0) * VV(0, 0) + TT(0, 1) * VV(0, 1) + TT(0, 2) * VV(0, 2)) * dL_da +
+		                      (TT(1, 0) * VV(0, 0) + TT(1, 1) * VV(0, 1) + TT(1, 2) * VV(0, 2)) * dL_db;
+		const float dL_dT01 = 2 * (TT(0, 0) * VV(1, 0) + TT(0, 1) * VV(1, 1) + TT(0, 2) * VV(1, 2)) * dL_da +
+		                      (TT(1, 0) * VV(1, 0) + TT(1, 1) * VV(1, 1) + TT(1, 2) * VV(1, 2)) * dL_db;
+		const float dL_dT02 = 2 * (TT(0, 0) * VV(2, 0) + TT(0, 1) * VV(2, 1) + TT(0, 2) * VV(2, 2)) * dL_da +
+		                      (TT(1, 0) * VV(2, 0) + TT(1, 1) * VV(2, 1) + TT(1, 2) * VV(2, 2)) * dL_db;
+		const float dL_dT10 = 2 * (TT(1, 0) * VV(0, 0) + TT(1, 1) * VV(0, 1) + TT(1, 2) * VV(0, 2)) * dL_dc +
+		                      (TT(0, 0) * VV(0, 0) + TT(0, 1) * VV(0, 1) + TT(0, 2) * VV(0, 2)) * dL_db;
+		const float dL_dT11 = 2 * (TT(1, 0) * VV(1, 0) + TT(1, 1) * VV(1, 1) + TT(1, 2) * VV(1, 2)) * dL_dc +
+		                      (TT(0, 0) * VV(1, 0) + TT(0, 1) * VV(1, 1) + TT(0, 2) * VV(1, 2)) * dL_db;
+		const float dL_dT12 = 2 * (TT(1, 0) * VV(2, 0) + TT(1, 1) * VV(2, 1) + TT(1, 2) * VV(2, 2)) * dL_dc +
+		                      (TT(0, 0) * VV(2, 0) + TT(0, 1) * VV(2, 1) + TT(0, 2) * VV(2, 2)) * dL_db;
+#undef TT
+#undef VV
+		const float dL_dJ00 = at(Wm, 0, 0) * dL_dT00 + at(Wm, 0, 1) * dL_dT01 + at(Wm, 0, 2) * dL_dT02;
+		const float dL_dJ02 = at(Wm, 2, 0) * dL_dT00 + at(Wm, 2, 1) * dL_dT01 + at(Wm, 2, 2) * dL_dT02;
+		const float dL_dJ11 = at(Wm, 1, 0) * dL_dT10 + at(Wm, 1, 1) * dL_dT11 + at(Wm, 1, 2) * dL_dT12;
+		const float dL_dJ12 = at(Wm, 2, 0) * dL_dT10 + at(Wm, 2, 1) * dL_dT11 + at(Wm, 2, 2) * dL_dT12;
+
+		const float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+		const float l3 = l * l * l;
+		// dL_dnJ[c][r] = dcn_r * rn_c
+		const float nJ02 = dcn.z * rn.x, nJ12 = dcn.z * rn.y, nJ20 = dcn.x * rn.z, nJ21 = dcn.y * rn.z, nJ22 = dcn.z * rn.z;
+		const float nJ00 = dcn.x * rn.x, nJ11 = dcn.y * rn.y;
+		const float dL_dtx = x_grad_mul * (-h_x * tz2 * dL_dJ02 + dL_du * tz - nJ02 * tz2 + nJ20 * (1 / l - t.x * t.x / l3) + nJ21 * (-t.x * t.y / l3) +
+		                                   nJ22 * (-t.x * t.z / l3) + (dcp0.x * plane0 + dcp0.y * plane1 + dcp2.x) / nl + dL_dl * t.x / l);
+		const float dL_dty = y_grad_mul * (-h_y * tz2 * dL_dJ12 + dL_dv * tz - nJ12 * tz2 + nJ20 * (-t.x * t.y / l3) + nJ21 * (1 / l - t.y * t.y / l3) +
+		                                   nJ22 * (-t.y * t.z / l3) + (dcp1.x * plane0 + dcp1.y * plane1 + dcp2.y) / nl + dL_dl * t.y / l);
+		const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12 -
+		                     (dL_du * t.x + dL_dv * t.y) * tz2 + (nJ00 + nJ11) * (-tz2) + nJ02 * (2 * t.x * tz3) + nJ12 * (2 * t.y * tz3) +
+		                     (nJ20 * t.x + nJ21 * t.y) * (-t.z / l3) + nJ22 * (1 / l - t.z * t.z / l3) +
+		                     (dcp0.x * (-(v2 + 1)) + dcp0.y * uv + dcp1.x * uv + dcp1.y * (-(u2 + 1)) + dcp2.x * plane0 + dcp2.y * plane1) / nl +
+		                     dL_dl * t.z / l;
+		float3 dL_dmean = xformvec4x3T(float3{dL_dtx, dL_dty, dL_dtz}, V);
+
+		// ---- screen-space mean, ray length and view-point terms (backward.cu:587-619) ----
+		{
+			const float* proj = p.projmatrix;
+			const float4 m_hom = xform4x4(mean, proj);
+			const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+			const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+			const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+			float3 d1;
+			d1.x = (proj[0] * m_w - proj[3] * mul1) * dL_dmean2D.x + (proj[1] * m_w - proj[3] * mul2) * dL_dmean2D.y;
+			d1.y = (proj[4] * m_w - proj[7] * mul1) * dL_dmean2D.x + (proj[5] * m_w - proj[7] * mul2) * dL_dmean2D.y;
+			d1.z = (proj[8] * m_w - proj[11] * mul1) * dL_dmean2D.x + (proj[9] * m_w - proj[11] * mul2) * dL_dmean2D.y;
+			const float3 m_view = xform4x3(mean, V);
+			const float tl = sqrt(m_view.x * m_view.x + m_view.y * m_view.y + m_view.z * m_view.z);
+			const float3 d2 = xformvec4x3T(float3{dL_dview_point.x + m_view.x / tl * dL_dts, dL_dview_point.y + m_view.y / tl * dL_dts,
+			                                      dL_dview_point.z + m_view.z / tl * dL_dts}, V);
+			dL_dmean.x += d1.x + d2.x;
+			dL_dmean.y += d1.y + d2.y;
+			dL_dmean.z += d1.z + d2.z;
+		}
+
+		// ---- SH backward (backward.cu:21-140) ----
+		if (p.shs != nullptr) {
+			const float3 campos = {p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]};
+			const float3 dir_orig = {mean.x - campos.x, mean.y - campos.y, mean.z - campos.z};
+			const float dlen = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+			const float x = dir_orig.x / dlen, y = dir_orig.y / dlen, z = dir_orig.z / dlen;
+			const uint8_t cb = g.clamped[idx];
+			const float dRGB[3] = {(cb & 1) ? 0.f : o_colors[0], (cb & 2) ? 0.f : o_colors[1], (cb & 4) ? 0.f : o_colors[2]};
+			const float* sh = p.shs + (size_t)idx * M * 3;
+			float* dsh = out.d_sh + (size_t)idx * M * 3;
+			const int deg = p.D;
+			float basis[16];
+			float ddx[16], ddy[16], ddz[16];  // d(basis_k)/d(dir)
+#pragma unroll
+			for (int k = 0; k < 16; k++) { basis[k] = 0.f; ddx[k] = 0.f; ddy[k] = 0.f; ddz[k] = 0.f; }
+			basis[0] = kSH0;
+			if (deg > 0) {
+				basis[1] = -kSH1 * y; basis[2] = kSH1 * z; basis[3] = -kSH1 * x;
+				ddx[3] = -kSH1; ddy[1] = -kSH1; ddz[2] = kSH1;
+				if (deg > 1) {
+					const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+					basis[4] = kSH2[0] * xy; basis[5] = kSH2[1] * yz; basis[6] = kSH2[2] * (2.f * zz - xx - yy);
+					basis[7] = kSH2[3] * xz; basis[8] = kSH2[4] * (xx - yy);
+					ddx[4] = kSH2[0] * y; ddx[6] = kSH2[2] * 2.f * -x; ddx[7] = kSH2[3] * z; ddx[8] = kSH2[4] * 2.f * x;
+					ddy[4] = kSH2[0] * x; ddy[5] = kSH2[1] * z; ddy[6] = kSH2[2] * 2.f * -y; ddy[8] = kSH2[4] * 2.f * -y;
+					ddz[5] = kSH2[1] * y; ddz[6] = kSH2[2] * 2.f * 2.f * z; ddz[7] = kSH2[3] * x;
+					if (deg > 2) {
+						basis[9] = kSH3[0] * y * (3.f * xx - yy); basis[10] = kSH3[1] * xy * z;
+						basis[11] = kSH3[2] * y * (4.f * zz - xx - yy); basis[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+						basis[13] = kSH3[4] * x * (4.f * zz - xx - yy); basis[14] = kSH3[5] * z * (xx - yy);
+						basis[15] = kSH3[6] * x * (xx - 3.f * yy);
+						ddx[9] = kSH3[0] * 3.f * 2.f * xy; ddx[10] = kSH3[1] * yz; ddx[11] = kSH3[2] * -2.f * xy; ddx[12] = kSH3[3] * -3.f * 2.f * xz;
+						ddx[13] = kSH3[4] * (-3.f * xx + 4.f * zz - yy); ddx[14] = kSH3[5] * 2.f * xz; ddx[15] = kSH3[6] * 3.f * (xx - yy);
+						ddy[9] = kSH3[0] * 3.f * (xx - yy); ddy[10] = kSH3[1] * xz; ddy[11] = kSH3[2] * (-3.f * yy + 4.f * zz - xx);
+						ddy[12] = kSH3[3] * -3.f * 2.f * yz; ddy[13] = kSH3[4] * -2.f * xy; ddy[14] = kSH3[5] * -2.f * yz; ddy[15] = kSH3[6] * -3.f * 2.f * xy;
+						ddz[10] = kSH3[1] * xy; ddz[11] = kSH3[2] * 4.f * 2.f * yz; ddz[12] = kSH3[3] * 3.f * (2.f * zz - xx - yy);
+						ddz[13] = kSH3[4] * 4.f * 2.f * xz; ddz[14] = kSH3[5] * (xx - yy);
+					}
+				}
+			}
+			const int ncoef = (deg + 1) * (deg + 1);
+			float3 dL_ddir = {0.f, 0.f, 0.f};
+			for (int k = 0; k < M; k++) {
+				float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+				if (k < ncoef) {
+					o0 = basis[k] * dRGB[0]; o1 = basis[k] * dRGB[1]; o2 = basis[k] * dRGB[2];
+					if (k > 0) {
+						const float s0 = __ldg(sh + 3 * k), s1 = __ldg(sh + 3 * k + 1), s2 = __ldg(sh + 3 * k + 2);
+						const float sd = s0 * dRGB[0] + s1 * dRGB[1] + s2 * dRGB[2];
+						dL_ddir.x += ddx[k] * sd;
+						dL_ddir.y += ddy[k] * sd;
+						dL_ddir.z += ddz[k] * sd;
+					}
+				}
+				dsh[3 * k] = o0; dsh[3 * k + 1] = o1; dsh[3 * k + 2] = o2;
+			}
+			// through the normalisation of the view direction (auxiliary.h:123-133)
+			const float sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;
+			const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
+			dL_dmean.x += ((+sum2 - dir_orig.x * dir_orig.x) * dL_ddir.x - dir_orig.y * dir_orig.x * dL_ddir.y - dir_orig.z * dir_orig.x * dL_ddir.z) * invsum32;
+			dL_dmean.y += (-dir_orig.x * dir_orig.y * dL_ddir.x + (sum2 - dir_orig.y * dir_orig.y) * dL_ddir.y - dir_orig.z * dir_orig.y * dL_ddir.z) * invsum32;
+			dL_dmean.z += (-dir_orig.x * dir_orig.z * dL_ddir.x - dir_orig.y * dir_orig.z * dL_ddir.y + (sum2 - dir_orig.z * dir_orig.z) * dL_ddir.z) * invsum32;
+		}
+		o_mean3D[0] = dL_dmean.x; o_mean3D[1] = dL_dmean.y; o_mean3D[2] = dL_dmean.z;
+
+		// ---- covariance -> scale / rotation (backward.cu:492-555) ----
+		if (from_scales) {
+			// M = S * Rg (glm), dL_dM = 2 M dL_dSigma ; dL_dMt = transpose(dL_dM)
+			M3 S = m3(s_mod.x, 0.f, 0.f, 0.f, s_mod.y, 0.f, 0.f, 0.f, s_mod.z);
+			M3 Mm = S * Rg;
+			M3 dSig = m3(o_cov[0], 0.5f * o_cov[1], 0.5f * o_cov[2], 0.5f * o_cov[1], o_cov[3], 0.5f * o_cov[4], 0.5f * o_cov[2], 0.5f * o_cov[4], o_cov[5]);
+			M3 dM = Mm * dSig;
+			dM.c[0] = dM.c[0] * 2.0f; dM.c[1] = dM.c[1] * 2.0f; dM.c[2] = dM.c[2] * 2.0f;
+			M3 Rt = transpose(Rg);
+			M3 dMt = transpose(dM);
+			o_scale[0] = dot3(Rt.c[0], dMt.c[0]);
+			o_scale[1] = dot3(Rt.c[1], dMt.c[1]);
+			o_scale[2] = dot3(Rt.c[2], dMt.c[2]);
+			dMt.c[0] = dMt.c[0] * s_mod.x;
+			dMt.c[1] = dMt.c[1] * s_mod.y;
+			dMt.c[2] = dMt.c[2] * s_mod.z;
+			const float r = q.x, x = q.y, y = q.z, z = q.w;
+#define D(c_, r_) at(dMt, c_, r_)
+			o_rot[0] = 2 * z * (D(0, 1) - D(1, 0)) + 2 * y * (D(2, 0) - D(0, 2)) + 2 * x * (D(1, 2) - D(2, 1));
+			o_rot[1] = 2 * y * (D(1, 0) + D(0, 1)) + 2 * z * (D(2, 0) + D(0, 2)) + 2 * r * (D(1, 2) - D(2, 1)) - 4 * x * (D(2, 2) + D(1, 1));
+			o_rot[2] = 2 * x * (D(1, 0) + D(0, 1)) + 2 * r * (D(2, 0) - D(0, 2)) + 2 * z * (D(1, 2) + D(2, 1)) - 4 * y * (D(2, 2) + D(0, 0));
+			o_rot[3] = 2 * r * (D(0, 1) - D(1, 0)) + 2 * x * (D(2, 0) + D(0, 2)) + 2 * y * (D(1, 2) + D(2, 1)) - 4 * z * (D(1, 1) + D(0, 0));
+#undef D
+			// the reference scales dL_dscale by nothing further: d(mod*s)/ds = mod is NOT applied (backward.cu:536-539)
+		}
+	}
+
+	// ---- write everything ----
+#pragma unroll
+	for (int i = 0; i < 3; i++) {
+		out.d_means2D[3 * idx + i] = o_means2D[i];
+		out.d_colors[3 * idx + i] = o_colors[i];
+		out.d_means3D[3 * idx + i] = o_mean3D[i];
+		out.d_scales[3 * idx + i] = o_scale[i];
+	}
+	out.d_opacity[idx] = o_opacity;
+#pragma unroll
+	for (int i = 0; i < 6; i++) out.d_cov3D[6 * idx + i] = o_cov[i];
+	*reinterpret_cast<float4*>(out.d_rotations + 4 * idx) = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
+}
+
+void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s) {
+	static const int fix_mip = getenv("RGS_FIX_MIP_GRADIENT") != nullptr && atoi(getenv("RGS_FIX_MIP_GRADIENT")) != 0;
+	preprocess_backward_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, grad_accum, out, fix_mip);
+	count_launch();
+}
+
+}  // namespace rgs

@@ -1,0 +1,335 @@
+// rgs_render_bwd.cu -- per-tile backward of the alpha blend for sm_100a.
+//
+// Replaces renderCUDA<3,COORD,DEPTH,NORMAL> backward (reference: cuda_rasterizer/backward.cu:631-1016,
+// dispatch :1101-1163).  The per-pixel recurrence (back-to-front re-traversal, T recovered by division,
+// running suffix blends, median terms) is the reference's; the gradient scatter is not:
+//   * the reference issues 10/16/22/25 scalar global atomicAdds per contributing (pixel, splat) pair
+//     (backward.cu:878-1013).  Here the 32 pixels of a warp evaluate the same splat in lock-step, the
+//     16 (or 32) per-splat partial gradients are combined with a recursive-halving shuffle
+//     reduce-scatter (16 resp. 31 SHFL instead of 80 resp. 125 for a butterfly per value), and ONE
+//     coalesced red.global.add of 64 B (128 B) per (warp, splat) lands in a packed accumulator row;
+//   * constant factors (0.5*W, 0.5*H, 1/focal) are pulled out of the sums and applied once per Gaussian
+//     in backward-preprocess;
+//   * the tile list is cut at the block-wide maximum of last_contributor (nothing behind it can receive
+//     gradient, backward.cu:838-839), each warp additionally skips splats behind ITS maximum and splats
+//     that cannot reach alpha >= 1/255 inside its 8x4 pixel block (same conservative test as forward);
+//   * records are gathered with cp.async into a 2-stage ring, like forward, but walking the list from
+//     the back.
+#include "rgs_render_common.cuh"
+
+namespace rgs {
+
+namespace {
+
+// Recursive-halving reduce-scatter over a warp.  On return lane L holds, in v[0], the warp-wide sum of
+// value index (L >> 1) for N == 16 (both lanes of a pair hold it) or index L for N == 32.
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane) {
+	static_assert(N == 16 || N == 32, "16 or 32 values");
+#pragma unroll
+	for (int h = N / 2, mask = 16; h >= 1; h >>= 1, mask >>= 1) {
+		const bool upper = (lane & mask) != 0;
+#pragma unroll
+		for (int k = 0; k < h; k++) {
+			const float send = upper ? v[k] : v[k + h];
+			const float keep = upper ? v[k + h] : v[k];
+			v[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+		}
+	}
+	if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+}  // namespace
+
+template <bool COORD, bool DEPTH>
+__global__ void __launch_bounds__(NTHREADS) render_backward_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float* __restrict__ records,
+    int W, int H, int grid_x, int row_begin, float focal_x, float focal_y, const float* __restrict__ bg_color,
+    const float* __restrict__ alphas, const float* __restrict__ normalmap, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ accum_depth, const float* __restrict__ accum_coord, const float* __restrict__ normal_length,
+    const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_coords, const float* __restrict__ dL_dpixel_mcoords,
+    const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dpixel_mdepths, const float* __restrict__ dL_dalphas,
+    const float* __restrict__ dL_dpixel_normals, float* __restrict__ grad_accum) {
+	constexpr bool GEO = COORD || DEPTH;
+	constexpr int RFQ = COORD ? 6 : 4;
+	constexpr int GF = COORD ? GRAD_FLOATS_COORD : GRAD_FLOATS_BASE;
+	extern __shared__ float4 smem[];  // [2][RFQ][BATCH] records, then [2][BATCH] ids
+	int* s_ids = reinterpret_cast<int*>(smem + 2 * RFQ * BATCH);
+	__shared__ int s_block_last[NTHREADS / 32];
+
+	const int tid = threadIdx.x;
+	const int warp = tid >> 5, lane = tid & 31;
+	const int tile_x = blockIdx.x, tile_y = blockIdx.y + row_begin;
+	const int bx0 = tile_x * TILE_X + (warp & 1) * 8, by0 = tile_y * TILE_Y + (warp >> 1) * 4;
+	const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+	const bool inside = px < W && py < H;
+	const float pxf = (float)px, pyf = (float)py;
+	const float wx0 = (float)bx0, wx1 = (float)min(bx0 + 7, W - 1), wy0 = (float)by0, wy1 = (float)min(by0 + 3, H - 1);
+	const int pix_id = W * py + px;
+	const size_t HW = (size_t)H * W;
+
+	const uint2 range = ranges[tile_y * grid_x + tile_x];
+
+	// ---- per-pixel state from forward (backward.cu:704-781) ----
+	const float T_final = inside ? (1 - alphas[pix_id]) : 0;
+	const float w_final = inside ? alphas[pix_id] : 0;
+	float T = T_final;
+	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+	const int max_contributor = inside ? (int)n_contrib[pix_id + HW] : 0;
+
+	float dL_dpixel[3] = {0.f, 0.f, 0.f};
+	float dL_dpixel_coord[3] = {0.f, 0.f, 0.f}, dL_dpixel_mcoord[3] = {0.f, 0.f, 0.f};
+	float dL_dpixel_t = 0.f, dL_dpixel_mt = 0.f, dL_dalpha = 0.f;
+	float dL_dpixel_normal[3] = {0.f, 0.f, 0.f};
+	if (inside) {
+#pragma unroll
+		for (int i = 0; i < 3; i++) dL_dpixel[i] = dL_dpixels[i * HW + pix_id];
+		dL_dalpha = dL_dalphas[pix_id];
+		if constexpr (GEO) {
+			const float ww = w_final * w_final;
+			if constexpr (COORD) {
+#pragma unroll
+				for (int i = 0; i < 3; i++) {
+					const float g = dL_dpixel_coords[i * HW + pix_id];
+					dL_dalpha -= g * accum_coord[i * HW + pix_id] / ww;
+					dL_dpixel_coord[i] = g / w_final;
+					dL_dpixel_mcoord[i] = dL_dpixel_mcoords[i * HW + pix_id];
+				}
+			}
+			if constexpr (DEPTH) {
+				const float pnx = (pxf - W / 2.f) / focal_x, pny = (pyf - H / 2.f) / focal_y;
+				const float ln = sqrt(pnx * pnx + pny * pny + 1);
+				const float g = dL_dpixel_depths[pix_id];
+				dL_dalpha -= g * accum_depth[pix_id] / ww;
+				dL_dpixel_t = g / w_final / ln;
+				dL_dpixel_mt = dL_dpixel_mdepths[pix_id] / ln;
+			}
+			{
+				const float gx = dL_dpixel_normals[pix_id], gy = dL_dpixel_normals[HW + pix_id], gz = dL_dpixel_normals[2 * HW + pix_id];
+				const float nx = normalmap[pix_id], ny = normalmap[HW + pix_id], nz = normalmap[2 * HW + pix_id];
+				const float nlen = normal_length[pix_id];
+				if (nlen < 1.0E-12F) {
+					dL_dpixel_normal[0] = gx / 1.0E-12F;
+					dL_dpixel_normal[1] = gy / 1.0E-12F;
+					dL_dpixel_normal[2] = gz / 1.0E-12F;
+				} else {
+					const float d = gx * nx + gy * ny + gz * nz;
+					dL_dpixel_normal[0] = (gx - d * nx) / nlen;
+					dL_dpixel_normal[1] = (gy - d * ny) / nlen;
+					dL_dpixel_normal[2] = (gz - d * nz) / nlen;
+				}
+			}
+		}
+	}
+	float bg_dot_dpixel = 0;
+#pragma unroll
+	for (int i = 0; i < 3; i++) bg_dot_dpixel += bg_color[i] * dL_dpixel[i];
+
+	// ---- cut the list at the last splat that contributed to any pixel of the block / warp ----
+	int warp_last = last_contributor;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+	if (lane == 0) s_block_last[warp] = warp_last;
+	__syncthreads();
+	int n = 0;
+#pragma unroll
+	for (int w = 0; w < NTHREADS / 32; w++) n = max(n, s_block_last[w]);
+	n = min(n, (int)(range.y - range.x));  // defensive; last_contributor <= list length by construction
+	const int rounds = (n + BATCH - 1) / BATCH;
+
+	float accum_rec[3] = {0.f, 0.f, 0.f}, last_color[3] = {0.f, 0.f, 0.f};
+	float accum_coord_rec[3] = {0.f, 0.f, 0.f}, last_coord[3] = {0.f, 0.f, 0.f};
+	float accum_t_rec = 0.f, last_t = 0.f;
+	float accum_normal_rec[3] = {0.f, 0.f, 0.f}, last_normal[3] = {0.f, 0.f, 0.f};
+	float accum_alpha_rec = 0.f, last_alpha = 0.f;
+
+	const float ddelx_dx = 0.5 * W;
+	const float ddely_dy = 0.5 * H;
+
+	// staged index j of round i is list position  n-1 - (i*BATCH + j)
+	const size_t rec_stride = (size_t)RFQ * 4;
+	auto issue_gather = [&](int stage, int id) {
+		if (id >= 0) {
+			const float4* src = reinterpret_cast<const float4*>(records + (size_t)id * rec_stride);
+			float4* dst = smem + (size_t)stage * RFQ * BATCH + tid;
+#pragma unroll
+			for (int c = 0; c < RFQ; c++) cp_async16(dst + c * BATCH, src + c);
+		}
+		s_ids[stage * BATCH + tid] = id;
+		cp_async_commit();
+	};
+	int id_cur = (tid < n) ? (int)point_list[range.x + n - 1 - tid] : -1;
+	issue_gather(0, id_cur);
+	int id_next = (BATCH + tid < n) ? (int)point_list[range.x + n - 1 - BATCH - tid] : -1;
+
+	for (int i = 0; i < rounds; i++) {
+		cp_async_wait_all();
+		__syncthreads();
+		if (i + 1 < rounds) {
+			issue_gather((i + 1) & 1, id_next);
+			const int nxt = (i + 2) * BATCH + tid;
+			id_next = (nxt < n) ? (int)point_list[range.x + n - 1 - nxt] : -1;
+		}
+		const float4* s = smem + (size_t)(i & 1) * RFQ * BATCH;
+		const int* ids = s_ids + (i & 1) * BATCH;
+		const int cnt = min(BATCH, n - i * BATCH);
+		const int pos0 = n - 1 - i * BATCH;  // list position of staged index 0
+		if (pos0 - (cnt - 1) >= warp_last) continue;  // whole batch is behind this warp's last contributor
+
+		for (int c0 = 0; c0 < cnt; c0 += 32) {
+			const int j = c0 + lane;
+			bool hit = false;
+			if (j < cnt && (pos0 - j) < warp_last) {
+				const float4 a = s[j], b = s[BATCH + j];
+				hit = splat_hits_box(a.x, a.y, a.z, a.w, b.x, b.y, wx0, wx1, wy0, wy1);
+			}
+			unsigned m = __ballot_sync(0xffffffffu, hit);
+			while (m) {
+				const int bpos = __ffs(m) - 1;
+				m &= m - 1;
+				const int jj = c0 + bpos;
+				const int contributor = pos0 - jj;  // 0-based position in the tile list (backward.cu:837)
+				const float4 q0 = s[jj], q1 = s[BATCH + jj];
+				const float dx = q0.x - pxf, dy = q0.y - pyf;
+				const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+				bool ok = contributor < last_contributor && !(power > 0.0f);
+				const float G = expf(power);
+				const float alpha = min(0.99f, q1.y * G);
+				ok = ok && !(alpha < 1.0f / 255.0f);
+				if (!__any_sync(0xffffffffu, ok)) continue;
+
+				const float4 q2 = s[2 * BATCH + jj];
+				float gv[GF];
+#pragma unroll
+				for (int k = 0; k < GF; k++) gv[k] = 0.f;
+				if (ok) {
+					T = T / (1.f - alpha);
+					const float dchannel_dcolor = alpha * T;
+					float dL_dopa = 0.0f;
+					const float col[3] = {q2.y, q2.z, q2.w};
+#pragma unroll
+					for (int ch = 0; ch < 3; ch++) {
+						const float c = col[ch];
+						accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+						last_color[ch] = c;
+						const float dL_dchannel = dL_dpixel[ch];
+						dL_dopa += (c - accum_rec[ch]) * dL_dchannel;
+						gv[G_COL + ch] = dchannel_dcolor * dL_dchannel;
+					}
+					float dL_dcoords[3] = {0.f, 0.f, 0.f};
+					float dL_dt = 0.f;
+					float4 q3, q4, q5;
+					if constexpr (GEO) q3 = s[3 * BATCH + jj];
+					if constexpr (COORD) {
+						q4 = s[4 * BATCH + jj];
+						q5 = s[5 * BATCH + jj];
+						const float coord[3] = {q4.x + q4.w * dx + q5.x * dy, q4.y + q5.y * dx + q5.z * dy, q4.z + q5.w * dx + q3.w * dy};
+#pragma unroll
+						for (int ch = 0; ch < 3; ch++) {
+							const float c = coord[ch];
+							accum_coord_rec[ch] = last_alpha * last_coord[ch] + (1.f - last_alpha) * accum_coord_rec[ch];
+							last_coord[ch] = c;
+							const float dL_dchannel = dL_dpixel_coord[ch];
+							dL_dopa += (c - accum_coord_rec[ch]) * dL_dchannel;
+							dL_dcoords[ch] = dchannel_dcolor * dL_dchannel;
+							if (contributor == max_contributor - 1) dL_dcoords[ch] += dL_dpixel_mcoord[ch];
+							gv[G_VP + ch] = dL_dcoords[ch];
+							gv[G_CP + 2 * ch] = dL_dcoords[ch] * dx;      // 1/focal_x applied in backward-preprocess
+							gv[G_CP + 2 * ch + 1] = dL_dcoords[ch] * dy;  // 1/focal_y
+						}
+					}
+					if constexpr (DEPTH) {
+						const float t = q1.z + (q1.w * dx + q2.x * dy);
+						accum_t_rec = last_alpha * last_t + (1.f - last_alpha) * accum_t_rec;
+						last_t = t;
+						dL_dopa += (t - accum_t_rec) * dL_dpixel_t;
+						dL_dt = dchannel_dcolor * dL_dpixel_t;
+						if (contributor == max_contributor - 1) dL_dt += dL_dpixel_mt;
+						gv[G_T] = dL_dt;
+						gv[G_RAYX] = dL_dt * dx;
+						gv[G_RAYY] = dL_dt * dy;
+					}
+					if constexpr (GEO) {
+						const float nrm[3] = {q3.x, q3.y, q3.z};
+#pragma unroll
+						for (int ch = 0; ch < 3; ch++) {
+							const float c = nrm[ch];
+							accum_normal_rec[ch] = last_alpha * last_normal[ch] + (1.f - last_alpha) * accum_normal_rec[ch];
+							last_normal[ch] = c;
+							const float dL_dchannel = dL_dpixel_normal[ch];
+							dL_dopa += (c - accum_normal_rec[ch]) * dL_dchannel;
+							gv[G_NRM + ch] = dchannel_dcolor * dL_dchannel;
+						}
+					}
+					accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
+					dL_dopa += (1 - accum_alpha_rec) * dL_dalpha;
+					dL_dopa *= T;
+					last_alpha = alpha;
+					dL_dopa += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+					const float dL_dG = q1.y * dL_dopa;
+					const float gdx = G * dx, gdy = G * dy;
+					const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
+					const float dG_ddely = -gdy * q1.x - gdx * q0.w;
+					float dL_ddelx = dL_dG * dG_ddelx;
+					float dL_ddely = dL_dG * dG_ddely;
+					if constexpr (COORD) {
+						dL_ddelx += dL_dcoords[0] * q4.w + dL_dcoords[1] * q5.y + dL_dcoords[2] * q5.w;
+						dL_ddely += dL_dcoords[0] * q5.x + dL_dcoords[1] * q5.z + dL_dcoords[2] * q3.w;
+					}
+					if constexpr (DEPTH) {
+						dL_ddelx += dL_dt * q1.w;
+						dL_ddely += dL_dt * q2.x;
+					}
+					gv[G_MX] = dL_ddelx;  // * 0.5 W in backward-preprocess
+					gv[G_MY] = dL_ddely;  // * 0.5 H
+					gv[G_MABS] = abs(dL_dG * dG_ddelx * ddelx_dx) + abs(dL_dG * dG_ddely * ddely_dy);
+					gv[G_CONX] = -0.5f * gdx * dx * dL_dG;
+					gv[G_CONY] = -0.5f * gdx * dy * dL_dG;
+					gv[G_CONW] = -0.5f * gdy * dy * dL_dG;
+					gv[G_OPA] = G * dL_dopa;
+				}
+				warp_reduce_scatter<GF>(gv, lane);
+				float* row = grad_accum + (size_t)ids[jj] * GF;
+				if (GF == 16) {
+					if ((lane & 1) == 0) atomicAdd(row + (lane >> 1), gv[0]);
+				} else {
+					if (lane < 25) atomicAdd(row + lane, gv[0]);
+				}
+			}
+		}
+	}
+}
+
+template <bool COORD, bool DEPTH>
+static void launch_variant(const FwdParams& p, GeomView g, BinView b, ImgView img, RenderGradIn gin, float* grad_accum, cudaStream_t s) {
+	constexpr int RFQ = COORD ? 6 : 4;
+	const size_t smem = (size_t)2 * RFQ * BATCH * sizeof(float4) + (size_t)2 * BATCH * sizeof(int);
+	auto kern = render_backward_kernel<COORD, DEPTH>;
+	static bool configured = false;
+	if (!configured) {
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		configured = true;
+	}
+	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
+	kern<<<grid, NTHREADS, smem, s>>>(img.ranges, b.point_list, g.records, p.W, p.H, p.grid_x, p.row_begin, p.focal_x, p.focal_y, p.background,
+	                                 gin.out_alpha, gin.out_normal, img.n_contrib, img.accum_depth, img.accum_coord, img.normal_length,
+	                                 gin.d_color, gin.d_coord, gin.d_mcoord, gin.d_depth, gin.d_mdepth, gin.d_alpha, gin.d_normal, grad_accum);
+	count_launch();
+}
+
+void launch_render_backward(const FwdParams& p, GeomView g, BinView b, ImgView img, RenderGradIn gin, float* grad_accum, cudaStream_t s) {
+	cudaMemsetAsync(grad_accum, 0, (size_t)p.P * grad_floats(p.coord) * sizeof(float), s);
+	count_launch();
+	if (p.row_end <= p.row_begin) return;
+	if (p.coord && p.depth)
+		launch_variant<true, true>(p, g, b, img, gin, grad_accum, s);
+	else if (p.coord)
+		launch_variant<true, false>(p, g, b, img, gin, grad_accum, s);
+	else if (p.depth)
+		launch_variant<false, true>(p, g, b, img, gin, grad_accum, s);
+	else
+		launch_variant<false, false>(p, g, b, img, gin, grad_accum, s);
+}
+
+}  // namespace rgs

@@ -1,0 +1,384 @@
+// torch_glue.cpp -- pybind11 module `diff_gaussian_rasterization._C` on top of the C ABI.
+//
+// Drop-in for the reference's torch glue: same four Python-callable symbols, argument order, tuple layouts
+// and error behaviour (reference: submodules/diff-gaussian-rasterization/rasterize_points.{h,cu},
+// ext.cpp:15-20).  Everything that touches the GPU goes through include/rgs_b200.h; this file only
+// allocates tensors, converts the "empty tensor == absent" convention to NULL pointers and forwards.
+//
+// Differences that are deliberate:
+//   * outputs are allocated with empty(): the kernels write every element (the reference zero-fills 15 image
+//     planes and 14 gradient tensors first, rasterize_points.cu:71-78,180-193);
+//   * work is queued on torch's CURRENT stream of the tensors' device (the reference uses the legacy default
+//     stream);
+//   * three extra symbols (`*_slab`, `*_backward_render`, `*_backward_preprocess`) expose the tile-row slab and
+//     the two backward stages for the multi-GPU path; the reference has no equivalent.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <string>
+#include <tuple>
+
+#include "rgs_b200.h"
+
+namespace {
+
+const float* opt_ptr(const torch::Tensor& t) { return t.numel() == 0 ? nullptr : t.data_ptr<float>(); }
+
+torch::Tensor as_input(const torch::Tensor& t, const torch::Tensor& like, const char* name) {
+	if (t.numel() == 0) return t;  // absent (torch.Tensor([]) on the CPU), stays absent
+	TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be float32");
+	TORCH_CHECK(t.device() == like.device(), name, " must be on the same device as means3D");
+	return t.contiguous();
+}
+
+char* resize_cb(void* user, size_t bytes) {
+	auto* t = reinterpret_cast<torch::Tensor*>(user);
+	t->resize_({(long long)bytes});
+	return reinterpret_cast<char*>(t->data_ptr());
+}
+
+void check(int64_t rc) {
+	if (rc < 0) throw std::runtime_error(std::string(rgs_last_error()));
+}
+
+struct CamHolder {
+	torch::Tensor bg, view, proj, campos;
+	rgs_camera cam;
+};
+
+void fill_camera(CamHolder& h, const torch::Tensor& like, const torch::Tensor& background, const torch::Tensor& viewmatrix,
+                 const torch::Tensor& projmatrix, const torch::Tensor& campos, float tan_fovx, float tan_fovy, float kernel_size,
+                 float scale_modifier, int H, int W, int degree, int M, bool prefiltered, bool require_coord, bool require_depth, bool debug,
+                 int row_begin, int row_end) {
+	h.bg = as_input(background, like, "background");
+	h.view = as_input(viewmatrix, like, "viewmatrix");
+	h.proj = as_input(projmatrix, like, "projmatrix");
+	h.campos = as_input(campos, like, "campos");
+	rgs_camera& c = h.cam;
+	c.width = W;
+	c.height = H;
+	c.tan_fovx = tan_fovx;
+	c.tan_fovy = tan_fovy;
+	c.kernel_size = kernel_size;
+	c.scale_modifier = scale_modifier;
+	c.viewmatrix = h.view.data_ptr<float>();
+	c.projmatrix = h.proj.data_ptr<float>();
+	c.cam_pos = h.campos.data_ptr<float>();
+	c.background = h.bg.data_ptr<float>();
+	c.sh_degree = degree;
+	c.sh_coeffs = M;
+	c.require_coord = require_coord;
+	c.require_depth = require_depth;
+	c.prefiltered = prefiltered;
+	c.debug = debug;
+	c.tile_row_begin = row_begin;
+	c.tile_row_end = row_end;
+}
+
+struct GaussHolder {
+	torch::Tensor means, opac, sh, colors, scales, rots, cov;
+	rgs_gaussians g;
+};
+
+void fill_gaussians(GaussHolder& h, const torch::Tensor& means3D, const torch::Tensor& opacity, const torch::Tensor& sh, const torch::Tensor& colors,
+                    const torch::Tensor& scales, const torch::Tensor& rotations, const torch::Tensor& cov3D_precomp) {
+	h.means = as_input(means3D, means3D, "means3D");
+	h.opac = as_input(opacity, means3D, "opacity");
+	h.sh = as_input(sh, means3D, "sh");
+	h.colors = as_input(colors, means3D, "colors_precomp");
+	h.scales = as_input(scales, means3D, "scales");
+	h.rots = as_input(rotations, means3D, "rotations");
+	h.cov = as_input(cov3D_precomp, means3D, "cov3D_precomp");
+	h.g.P = (int)means3D.size(0);
+	h.g.means3D = opt_ptr(h.means);
+	h.g.opacities = opt_ptr(h.opac);
+	h.g.shs = opt_ptr(h.sh);
+	h.g.colors_precomp = opt_ptr(h.colors);
+	h.g.scales = opt_ptr(h.scales);
+	h.g.rotations = opt_ptr(h.rots);
+	h.g.cov3D_precomp = opt_ptr(h.cov);
+}
+
+using FwdResult = std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+                             torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>;
+
+FwdResult forward_impl(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors, const torch::Tensor& opacity,
+                       const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                       const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                       const float kernel_size, const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
+                       const torch::Tensor& campos, const bool prefiltered, const bool require_coord, const bool require_depth, const bool debug,
+                       int row_begin, int row_end) {
+	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
+		AT_ERROR("means3D must have dimensions (num_points, 3)");
+	}
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor: this rasterizer has no CPU path");
+	const c10::cuda::CUDAGuard guard(means3D.device());
+	const int P = means3D.size(0);
+	const int H = image_height, W = image_width;
+	auto int_opts = means3D.options().dtype(torch::kInt32);
+	auto float_opts = means3D.options().dtype(torch::kFloat32);
+	auto byte_opts = means3D.options().dtype(torch::kByte);
+	const int grid_y = (H + 15) / 16;
+	const bool whole = (row_begin == 0 && (row_end < 0 || row_end == grid_y));
+	const bool fill = (P == 0) || !whole;  // P == 0: the reference returns all-zero maps (rasterize_points.cu:90)
+	auto img = [&](int ch) { return fill ? torch::zeros({ch, H, W}, float_opts) : torch::empty({ch, H, W}, float_opts); };
+	torch::Tensor out_color = img(3), out_depth = img(1), out_mdepth = img(1), out_coord = img(3), out_mcoord = img(3), out_alpha = img(1),
+	              out_normal = img(3);
+	torch::Tensor radii = P == 0 ? torch::zeros({P}, int_opts) : torch::empty({P}, int_opts);
+	torch::Tensor geomBuffer = torch::empty({0}, byte_opts), binningBuffer = torch::empty({0}, byte_opts), imgBuffer = torch::empty({0}, byte_opts);
+
+	int rendered = 0;
+	if (P != 0) {
+		int M = 0;
+		if (sh.size(0) != 0) M = sh.size(1);
+		CamHolder ch;
+		fill_camera(ch, means3D, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, kernel_size, scale_modifier, H, W, degree, M,
+		            prefiltered, require_coord, require_depth, debug, row_begin, row_end);
+		GaussHolder gh;
+		fill_gaussians(gh, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp);
+		rgs_forward_out fo{out_color.data_ptr<float>(), out_coord.data_ptr<float>(), out_mcoord.data_ptr<float>(), out_alpha.data_ptr<float>(),
+		                   out_normal.data_ptr<float>(), out_depth.data_ptr<float>(), out_mdepth.data_ptr<float>(), radii.data_ptr<int>()};
+		rgs_buffers bufs{resize_cb, &geomBuffer, resize_cb, &binningBuffer, resize_cb, &imgBuffer};
+		const int64_t rc = rgs_forward(&ch.cam, &gh.g, &fo, &bufs, at::cuda::getCurrentCUDAStream().stream());
+		check(rc);
+		rendered = (int)rc;
+	}
+	return std::make_tuple(rendered, out_color, out_coord, out_mcoord, out_alpha, out_normal, out_depth, out_mdepth, radii, geomBuffer,
+	                       binningBuffer, imgBuffer);
+}
+
+// ---- the reference's four symbols ------------------------------------------------------------------------------
+
+FwdResult RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                                 const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                 const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                 const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const float kernel_size,
+                                 const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
+                                 const torch::Tensor& campos, const bool prefiltered, const bool require_coord, const bool require_depth,
+                                 const bool debug) {
+	return forward_impl(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+	                    tan_fovy, kernel_size, image_height, image_width, sh, degree, campos, prefiltered, require_coord, require_depth, debug, 0, -1);
+}
+
+struct BackwardCtx {
+	CamHolder ch;
+	GaussHolder gh;
+	torch::Tensor g_color, g_coord, g_mcoord, g_depth, g_mdepth, g_alpha, g_normal, normalmap, alphas, radii, geom, binning, image;
+	rgs_backward_in in;
+};
+
+void fill_backward(BackwardCtx& c, const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                   const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
+                   const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx,
+                   const float tan_fovy, const float kernel_size, const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_coord,
+                   const torch::Tensor& dL_dout_mcoord, const torch::Tensor& dL_dout_depth, const torch::Tensor& dL_dout_mdepth,
+                   const torch::Tensor& dL_dout_alpha, const torch::Tensor& dL_dout_normal, const torch::Tensor& normalmap, const torch::Tensor& sh,
+                   const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
+                   const torch::Tensor& imageBuffer, const torch::Tensor& alphas, const bool require_coord, const bool require_depth,
+                   const bool debug, int row_begin, int row_end) {
+	const int H = dL_dout_color.size(1), W = dL_dout_color.size(2);
+	int M = 0;
+	if (sh.size(0) != 0) M = sh.size(1);
+	fill_camera(c.ch, means3D, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, kernel_size, scale_modifier, H, W, degree, M, false,
+	            require_coord, require_depth, debug, row_begin, row_end);
+	torch::Tensor no_opacity = torch::empty({0});  // backward does not receive the opacities (rasterize_points.h:43-76)
+	fill_gaussians(c.gh, means3D, no_opacity, sh, colors, scales, rotations, cov3D_precomp);
+	c.g_color = as_input(dL_dout_color, means3D, "dL_dout_color");
+	c.g_coord = as_input(dL_dout_coord, means3D, "dL_dout_coord");
+	c.g_mcoord = as_input(dL_dout_mcoord, means3D, "dL_dout_mcoord");
+	c.g_depth = as_input(dL_dout_depth, means3D, "dL_dout_depth");
+	c.g_mdepth = as_input(dL_dout_mdepth, means3D, "dL_dout_mdepth");
+	c.g_alpha = as_input(dL_dout_alpha, means3D, "dL_dout_alpha");
+	c.g_normal = as_input(dL_dout_normal, means3D, "dL_dout_normal");
+	c.normalmap = as_input(normalmap, means3D, "normalmap");
+	c.alphas = as_input(alphas, means3D, "alphas");
+	c.radii = radii.contiguous();
+	c.geom = geomBuffer.contiguous();
+	c.binning = binningBuffer.contiguous();
+	c.image = imageBuffer.contiguous();
+	c.in.dL_dout_color = c.g_color.data_ptr<float>();
+	c.in.dL_dout_coord = c.g_coord.data_ptr<float>();
+	c.in.dL_dout_mcoord = c.g_mcoord.data_ptr<float>();
+	c.in.dL_dout_depth = c.g_depth.data_ptr<float>();
+	c.in.dL_dout_mdepth = c.g_mdepth.data_ptr<float>();
+	c.in.dL_dout_alpha = c.g_alpha.data_ptr<float>();
+	c.in.dL_dout_normal = c.g_normal.data_ptr<float>();
+	c.in.out_alpha = c.alphas.data_ptr<float>();
+	c.in.out_normal = c.normalmap.data_ptr<float>();
+	c.in.radii = c.radii.data_ptr<int>();
+	c.in.geom_buffer = reinterpret_cast<const char*>(c.geom.data_ptr());
+	c.in.binning_buffer = reinterpret_cast<const char*>(c.binning.data_ptr());
+	c.in.image_buffer = reinterpret_cast<const char*>(c.image.data_ptr());
+	c.in.num_rendered = R;
+}
+
+using BwdResult = std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>;
+
+struct GradTensors {
+	torch::Tensor means3D, means2D, colors, opacity, cov3D, sh, scales, rotations;
+	rgs_backward_out out;
+};
+
+void alloc_grads(GradTensors& t, const torch::Tensor& means3D, int P, int M) {
+	auto o = means3D.options();
+	auto mk = [&](std::initializer_list<int64_t> shape) { return P == 0 ? torch::zeros(shape, o) : torch::empty(shape, o); };
+	t.means3D = mk({P, 3});
+	t.means2D = mk({P, 3});
+	t.colors = mk({P, 3});
+	t.opacity = mk({P, 1});
+	t.cov3D = mk({P, 6});
+	t.sh = mk({P, M, 3});
+	t.scales = mk({P, 3});
+	t.rotations = mk({P, 4});
+	t.out.dL_dmeans2D = t.means2D.data_ptr<float>();
+	t.out.dL_dcolors = t.colors.data_ptr<float>();
+	t.out.dL_dopacity = t.opacity.data_ptr<float>();
+	t.out.dL_dmeans3D = t.means3D.data_ptr<float>();
+	t.out.dL_dcov3D = t.cov3D.data_ptr<float>();
+	t.out.dL_dsh = M > 0 ? t.sh.data_ptr<float>() : nullptr;
+	t.out.dL_dscales = t.scales.data_ptr<float>();
+	t.out.dL_drotations = t.rotations.data_ptr<float>();
+}
+
+BwdResult RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                                         const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                         const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                         const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const float kernel_size,
+                                         const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_coord,
+                                         const torch::Tensor& dL_dout_mcoord, const torch::Tensor& dL_dout_depth,
+                                         const torch::Tensor& dL_dout_mdepth, const torch::Tensor& dL_dout_alpha,
+                                         const torch::Tensor& dL_dout_normal, const torch::Tensor& normalmap, const torch::Tensor& sh,
+                                         const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+                                         const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const torch::Tensor& alphas,
+                                         const bool require_coord, const bool require_depth, const bool debug) {
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor: this rasterizer has no CPU path");
+	const c10::cuda::CUDAGuard guard(means3D.device());
+	const int P = means3D.size(0);
+	int M = 0;
+	if (sh.size(0) != 0) M = sh.size(1);
+	GradTensors gt;
+	alloc_grads(gt, means3D, P, M);
+	if (P != 0) {
+		BackwardCtx c;
+		fill_backward(c, background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+		              tan_fovy, kernel_size, dL_dout_color, dL_dout_coord, dL_dout_mcoord, dL_dout_depth, dL_dout_mdepth, dL_dout_alpha,
+		              dL_dout_normal, normalmap, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, alphas, require_coord, require_depth,
+		              debug, 0, -1);
+		torch::Tensor scratch = torch::empty({0}, means3D.options().dtype(torch::kByte));
+		check(rgs_backward(&c.ch.cam, &c.gh.g, &c.in, &gt.out, resize_cb, &scratch, at::cuda::getCurrentCUDAStream().stream()));
+	}
+	return std::make_tuple(gt.means2D, gt.colors, gt.opacity, gt.means3D, gt.cov3D, gt.sh, gt.scales, gt.rotations);
+}
+
+torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix) {
+	const int P = means3D.size(0);
+	torch::Tensor present = torch::full({P}, false, means3D.options().dtype(at::kBool));
+	if (P != 0) {
+		TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor: this rasterizer has no CPU path");
+		const c10::cuda::CUDAGuard guard(means3D.device());
+		torch::Tensor m = means3D.contiguous(), v = viewmatrix.contiguous(), pr = projmatrix.contiguous();
+		check(rgs_mark_visible(P, m.data_ptr<float>(), v.data_ptr<float>(), pr.data_ptr<float>(), reinterpret_cast<uint8_t*>(present.data_ptr<bool>()),
+		                       at::cuda::getCurrentCUDAStream().stream()));
+	}
+	return present;
+}
+
+// GOF-style opacity integration at query points (rasterize_points.h:83-107): used only by marching-tetrahedra
+// mesh extraction, outside this build's hot path (DESIGN.md "Out of scope").  The symbol is kept so that
+// `GaussianRasterizer.integrate` fails with a clear message instead of an AttributeError.
+py::object IntegrateGaussiansToPointsCUDA(py::args, py::kwargs) {
+	TORCH_CHECK(false, "integrate_gaussians_to_points is not implemented in the B200 rasterizer build (mesh-extraction path, out of scope)");
+	return py::none();
+}
+
+// ---- multi-GPU extras ---------------------------------------------------------------------------------------------
+
+FwdResult RasterizeGaussiansSlabCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                                     const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                     const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                     const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const float kernel_size,
+                                     const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
+                                     const torch::Tensor& campos, const bool prefiltered, const bool require_coord, const bool require_depth,
+                                     const bool debug, const int tile_row_begin, const int tile_row_end) {
+	return forward_impl(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+	                    tan_fovy, kernel_size, image_height, image_width, sh, degree, campos, prefiltered, require_coord, require_depth, debug,
+	                    tile_row_begin, tile_row_end);
+}
+
+// stage 1: returns the packed screen-space gradient accumulator [P, rgs_grad_stride] (additive across slabs)
+torch::Tensor BackwardRenderCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                                 const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
+                                 const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
+                                 const float tan_fovx, const float tan_fovy, const float kernel_size, const torch::Tensor& dL_dout_color,
+                                 const torch::Tensor& dL_dout_coord, const torch::Tensor& dL_dout_mcoord, const torch::Tensor& dL_dout_depth,
+                                 const torch::Tensor& dL_dout_mdepth, const torch::Tensor& dL_dout_alpha, const torch::Tensor& dL_dout_normal,
+                                 const torch::Tensor& normalmap, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+                                 const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+                                 const torch::Tensor& alphas, const bool require_coord, const bool require_depth, const bool debug,
+                                 const int tile_row_begin, const int tile_row_end) {
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor: this rasterizer has no CPU path");
+	const c10::cuda::CUDAGuard guard(means3D.device());
+	const int P = means3D.size(0);
+	const int GS = rgs_grad_stride(require_coord, require_depth);
+	torch::Tensor acc = P == 0 ? torch::zeros({P, GS}, means3D.options()) : torch::empty({P, GS}, means3D.options());
+	if (P != 0) {
+		BackwardCtx c;
+		fill_backward(c, background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+		              tan_fovy, kernel_size, dL_dout_color, dL_dout_coord, dL_dout_mcoord, dL_dout_depth, dL_dout_mdepth, dL_dout_alpha,
+		              dL_dout_normal, normalmap, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, alphas, require_coord, require_depth,
+		              debug, tile_row_begin, tile_row_end);
+		check(rgs_backward_render(&c.ch.cam, &c.gh.g, &c.in, acc.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
+	}
+	return acc;
+}
+
+// stage 2: accumulator (after the cross-rank sum) -> the reference's 8-tuple of parameter gradients
+BwdResult BackwardPreprocessCUDA(const torch::Tensor& grad_accum, const torch::Tensor& background, const torch::Tensor& means3D,
+                                 const torch::Tensor& radii, const torch::Tensor& colors, const torch::Tensor& opacity, const torch::Tensor& scales,
+                                 const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                                 const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                                 const float kernel_size, const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
+                                 const torch::Tensor& campos, const torch::Tensor& geomBuffer, const bool require_coord, const bool require_depth,
+                                 const bool debug) {
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor: this rasterizer has no CPU path");
+	const c10::cuda::CUDAGuard guard(means3D.device());
+	const int P = means3D.size(0);
+	int M = 0;
+	if (sh.size(0) != 0) M = sh.size(1);
+	GradTensors gt;
+	alloc_grads(gt, means3D, P, M);
+	if (P != 0) {
+		CamHolder ch;
+		fill_camera(ch, means3D, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, kernel_size, scale_modifier, image_height,
+		            image_width, degree, M, false, require_coord, require_depth, debug, 0, -1);
+		GaussHolder gh;
+		fill_gaussians(gh, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp);
+		torch::Tensor acc = as_input(grad_accum, means3D, "grad_accum");
+		torch::Tensor geom = geomBuffer.contiguous(), rad = radii.contiguous();
+		rgs_backward_in in;
+		memset(&in, 0, sizeof(in));
+		in.radii = rad.data_ptr<int>();
+		in.geom_buffer = reinterpret_cast<const char*>(geom.data_ptr());
+		in.image_buffer = in.geom_buffer;    // not read by stage 2
+		in.binning_buffer = in.geom_buffer;  // not read by stage 2
+		check(rgs_backward_preprocess(&ch.cam, &gh.g, &in, acc.data_ptr<float>(), &gt.out, at::cuda::getCurrentCUDAStream().stream()));
+	}
+	return std::make_tuple(gt.means2D, gt.colors, gt.opacity, gt.means3D, gt.cov3D, gt.sh, gt.scales, gt.rotations);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+	m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
+	m.def("integrate_gaussians_to_points", &IntegrateGaussiansToPointsCUDA);
+	m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
+	m.def("mark_visible", &markVisible);
+	// extras (not in the reference)
+	m.def("rasterize_gaussians_slab", &RasterizeGaussiansSlabCUDA);
+	m.def("rasterize_gaussians_backward_render", &BackwardRenderCUDA);
+	m.def("rasterize_gaussians_backward_preprocess", &BackwardPreprocessCUDA);
+	m.def("grad_stride", [](bool require_coord, bool require_depth) { return rgs_grad_stride(require_coord, require_depth); });
+	m.def("launch_count", []() { return rgs_launch_count(); });
+	m.def("abi_version", []() { return rgs_abi_version(); });
+}
