@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 rasterizer (BASELINE.json: Mpix/s fwd+bwd @ 1M splats, 1600x1200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over one synthetic camera: `_C.rasterize_gaussians` followed by
+`_C.rasterize_gaussians_backward` with fixed upstream gradients.  Prints ONE JSON line (rank 0):
+  value        W*H*K / t  with every input resident in HBM (device-timed, max over ranks)
+  e2e          same metric through the public autograd API (`GaussianRasterizer`, what render() calls) with the
+               step's host inputs -- camera matrices and the ground-truth colour/depth/normal maps -- copied from
+               pinned host memory inside the timed region and the loss read back to the host every step
+  roofline     dominant kernel (backward render): algorithmic bytes / its average launch duration,
+               measured with CUDA events the library records on the launching stream in a second timed pass
+  cpu_baseline the CPU oracle port (oracle/oracle.c, 1 thread) on a bounded sample of the same workload, plus the
+               pure-torch config[0] plumbing timing -- reported, not a target
+`--impl reference` times the reference's own CUDA rasterizer (oracle/_ref/ref_dgr_C.so, built from /root/reference
+by oracle/build_ref.py) on the same config through the same harness: the reference has NO CPU implementation of
+this path, so its arm runs where it can -- on the GPU (see DESIGN.md "Measurement").
+N > 1: tile rows of the one image are sharded over the ranks (strong scaling), one NCCL all-reduce of the
+screen-space gradient rows per backward.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "rade-gs_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "Mpix/s fwd+bwd @1M splats 1600x1200"
+
+
+# ---- clocks ----------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi sampled in a thread during the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ---- implementations under test ----------------------------------------------------------------------------------
+
+def load_impl(name):
+    if name == "ours":
+        import diff_gaussian_rasterization as dgr
+        return dgr._C
+    import build_ref
+    return build_ref.load()
+
+
+class _RefFunction(torch.autograd.Function):
+    """Autograd adapter around a reference-style `_C` (same call sequence as the reference's Python wrapper,
+    diff_gaussian_rasterization/__init__.py:44-169); used for the reference arm's e2e number."""
+
+    @staticmethod
+    def forward(ctx, C, sc, coord, depth, ks, means3D, means2D, sh, opac, scales, rots):
+        E = torch.Tensor([])
+        out = C.rasterize_gaussians(sc["bg"], means3D, E, opac, scales, rots, 1.0, E, sc["view"], sc["proj"], sc["tanx"], sc["tany"], ks,
+                                    sc["H"], sc["W"], sh, 3, sc["campos"], False, coord, depth, False)
+        n, color, co, mco, alpha, normal, dep, mdep, radii, gb, bb, ib = out
+        ctx.C, ctx.sc, ctx.coord, ctx.depth, ctx.ks, ctx.n = C, sc, coord, depth, ks, n
+        ctx.save_for_backward(means3D, scales, rots, normal, radii, sh, gb, bb, ib, alpha)
+        return color, radii, co, mco, dep, mdep, alpha, normal
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_co, g_mco, g_dep, g_mdep, g_alpha, g_normal):
+        means3D, scales, rots, normal, radii, sh, gb, bb, ib, alpha = ctx.saved_tensors
+        sc, E = ctx.sc, torch.Tensor([])
+        g = ctx.C.rasterize_gaussians_backward(sc["bg"], means3D, radii, E, scales, rots, 1.0, E, sc["view"], sc["proj"], sc["tanx"], sc["tany"], ctx.ks,
+                                               g_color, g_co, g_mco, g_dep, g_mdep, g_alpha, g_normal, normal, sh, 3, sc["campos"], gb, ctx.n, bb, ib,
+                                               alpha, ctx.coord, ctx.depth, False)
+        g_means2D, g_colors, g_opac, g_means3D, g_cov, g_sh, g_scales, g_rots = g
+        return None, None, None, None, None, g_means3D, g_means2D, g_sh, g_opac, g_scales, g_rots
+
+
+def cpu_baseline():
+    """Bounded CPU work (about 10-20 s): the oracle port on a C2-density sample + config[0] torch plumbing."""
+    import numpy as np
+    import oracle
+    from rade_gs_b200 import scenes
+    Wd, Hd, P = 400, 300, 62_500   # 1/16 of C2's pixels and splats, same focal-per-pixel density (f scaled by 1/4)
+    sc = scenes.make_scene(P, Wd, Hd, 350.0, -4.6, seed=1234)
+    g = scenes.make_upstream_grads(Hd, Wd, seed=4321)
+    inp = oracle.Inputs(sc.means3D.numpy(), sc.opacities.numpy(), sc.viewmatrix.numpy(), sc.projmatrix.numpy(), sc.campos.numpy(), sc.bg.numpy(),
+                        Wd, Hd, sc.tanfovx, sc.tanfovy, shs=sc.shs.numpy(), scales=sc.scales.numpy(), rotations=sc.rotations.numpy(), sh_degree=3,
+                        require_depth=True)
+    oracle.lib()
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        f = oracle.forward(inp)
+        oracle.backward(inp, f, {k: v.numpy() for k, v in g.items()})
+        reps += 1
+        if time.perf_counter() - t0 > 10.0 or reps >= 50:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    res = {"value": Wd * Hd / dt / 1e6, "unit": "Mpix/s", "cores": 1, "kind": "port",
+           "sample": f"oracle/oracle.c fwd+bwd, {P} splats {Wd}x{Hd} (C2 scaled 1/16: same splats per pixel), {reps} reps, R={f['num_rendered']}"}
+    # config[0]: 1k Gaussians, torch-CPU cov3D (L L^T) + SH degree-0 colour + projection (plumbing only)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    s0 = scenes.make_scene(1000, 1600, 1200, 1400.0, -4.6)
+    t0 = time.perf_counter()
+    n0 = 200
+    for _ in range(n0):
+        r, x, y, z = s0.rotations.unbind(1)
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y), 2 * (x * y + r * z), 1 - 2 * (x * x + z * z),
+                         2 * (y * z - r * x), 2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).view(-1, 3, 3)
+        L = R * s0.scales[:, None, :]
+        cov = L @ L.transpose(1, 2)
+        col = (0.28209479177387814 * s0.shs[:, 0] + 0.5).clamp_min(0)
+        ph = torch.cat([s0.means3D, torch.ones(1000, 1)], 1) @ s0.projmatrix
+        ndc = ph[:, :3] / (ph[:, 3:] + 1e-7)
+        _ = cov.sum() + col.sum() + ndc.sum()
+    res["config0_torch_cpu"] = {"us_per_call": (time.perf_counter() - t0) / n0 * 1e6, "threads": torch.get_num_threads(),
+                                "what": "1k Gaussians: cov3D + SH deg-0 + projection in pure torch on CPU"}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference" and rank != 0:
+        return  # single-GPU reference: rank 0 alone runs it
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    multi = world > 1 and a.impl == "ours"
+    if multi:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from rade_gs_b200 import multigpu, rawapi, scenes
+    C = load_impl(a.impl)
+    sc_cpu, coord, depth = scenes.make_config(a.config)
+    sc = sc_cpu.to(dev)
+    W, H, P = sc.width, sc.height, sc.means3D.shape[0]
+    grads = scenes.make_upstream_grads(H, W, device=dev)
+    grid_y = (H + 15) // 16
+    slab = multigpu.partition_tile_rows(grid_y, world)[rank] if multi else (0, grid_y)
+    E = torch.Tensor([])
+
+    def step_resident():
+        if not multi:
+            f = rawapi.forward(C, sc, coord, depth)
+            return f, rawapi.backward(C, sc, f, grads)
+        out = C.rasterize_gaussians_slab(sc.bg, sc.means3D, E, sc.opacities, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix, sc.projmatrix,
+                                         sc.tanfovx, sc.tanfovy, 0.0, H, W, sc.shs, 3, sc.campos, False, coord, depth, False, slab[0], slab[1])
+        acc = C.rasterize_gaussians_backward_render(sc.bg, sc.means3D, out[8], E, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix, sc.projmatrix,
+                                                    sc.tanfovx, sc.tanfovy, 0.0, grads["color"], grads["coord"], grads["mcoord"], grads["depth"],
+                                                    grads["mdepth"], grads["alpha"], grads["normal"], out[5], sc.shs, 3, sc.campos, out[9], out[0],
+                                                    out[10], out[11], out[4], coord, depth, False, slab[0], slab[1])
+        dist.all_reduce(acc)
+        g = C.rasterize_gaussians_backward_preprocess(acc, sc.bg, sc.means3D, out[8], E, sc.opacities, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix,
+                                                      sc.projmatrix, sc.tanfovx, sc.tanfovy, 0.0, H, W, sc.shs, 3, sc.campos, out[9], coord, depth, False)
+        return {"num_rendered": out[0]}, g
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if multi:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, r
+
+    # ---- resident-input number ----
+    for _ in range(a.warmup):
+        last = step_resident()
+    launches0 = C.launch_count() if a.impl == "ours" else 0
+    with ClockSampler(local) as clk:
+        ms, last = timed(step_resident, a.steps)
+    launches = (C.launch_count() - launches0) if a.impl == "ours" else None
+    ms_per_step = ms / a.steps
+    value = W * H / (ms_per_step * 1e-3) / 1e6
+    R = int(last[0]["num_rendered"])
+
+    # ---- end-to-end number: public autograd API, host inputs copied in, loss copied out ----
+    import diff_gaussian_rasterization as dgr
+    host = {"view": sc_cpu.viewmatrix.pin_memory(), "proj": sc_cpu.projmatrix.pin_memory(), "campos": sc_cpu.campos.pin_memory(),
+            "bg": sc_cpu.bg.pin_memory(), "gt_color": torch.rand(3, H, W).pin_memory(), "gt_depth": (torch.rand(1, H, W) * 8 + 2).pin_memory(),
+            "gt_normal": torch.nn.functional.normalize(torch.randn(3, H, W), dim=0).pin_memory()}
+    h2d = sum(v.numel() * 4 for v in host.values())
+    dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    leaves = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    copy_stream = torch.cuda.Stream(device=dev)
+    r0, r1 = min(slab[0] * 16, H), min(slab[1] * 16, H)
+
+    def step_e2e():
+        for k in ("view", "proj", "campos", "bg"):                 # camera: needed by forward, current stream
+            dbuf[k].copy_(host[k], non_blocking=True)
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):                        # ground truth: needed by the loss only -> overlaps forward
+            for k in ("gt_color", "gt_depth", "gt_normal"):
+                dbuf[k].copy_(host[k], non_blocking=True)
+        for t in leaves.values():
+            t.grad = None
+        means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        if a.impl == "ours":
+            st = dgr.GaussianRasterizationSettings(H, W, sc.tanfovx, sc.tanfovy, 0.0, dbuf["bg"], 1.0, dbuf["view"], dbuf["proj"], 3, dbuf["campos"],
+                                                   False, depth, coord, False)
+            rast = multigpu.ShardedGaussianRasterizer(st, rank=rank, world_size=world) if multi else dgr.GaussianRasterizer(st)
+            color, radii, co, mco, dep, mdep, alpha, normal = rast(leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"],
+                                                                    scales=leaves["scales"], rotations=leaves["rotations"])
+        else:
+            scd = {"bg": dbuf["bg"], "view": dbuf["view"], "proj": dbuf["proj"], "campos": dbuf["campos"], "tanx": sc.tanfovx, "tany": sc.tanfovy,
+                   "H": H, "W": W}
+            color, radii, co, mco, dep, mdep, alpha, normal = _RefFunction.apply(C, scd, coord, depth, 0.0, leaves["means3D"], means2D, leaves["shs"],
+                                                                                 leaves["opacities"], leaves["scales"], leaves["rotations"])
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        sl = slice(r0, r1)
+        loss = (color[:, sl] - dbuf["gt_color"][:, sl]).abs().mean() + 0.1 * (dep[:, sl] - dbuf["gt_depth"][:, sl]).abs().mean() + \
+            0.05 * (1 - (normal[:, sl] * dbuf["gt_normal"][:, sl]).sum(0)).mean()
+        loss.backward()
+        return float(loss.item())                                   # D2H read of the step's result
+
+    for _ in range(a.warmup):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, a.steps)
+    e2e_value = W * H / (ms_e2e / a.steps * 1e-3) / 1e6
+
+    # ---- per-stage device times (second pass, events recorded by the library on the launching stream) ----
+    roofline, stages = None, None
+    if a.impl == "ours" and hasattr(C, "stage_timing"):
+        C.stage_timing(True)
+        for _ in range(a.steps):
+            step_resident()
+        torch.cuda.synchronize()
+        stages = C.stage_times()          # {name: (total_ms, launches)}
+        C.stage_timing(False)
+        Pv = int((last_radii(C, sc, coord, depth) > 0).sum().item()) if not multi else None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        tot, n = stages.get("render_backward", (0.0, 0))
+        if n and Pv is not None:
+            tiles = ((W + 15) // 16) * grid_y
+            # R*(A_v+4) + N*I_v + 8*T + 4*G_v*Pv   (depth variant: A=60, I=68, G=16; coord: 84/92/22; both: 96/104/25)
+            A, I, G = {(False, False): (36, 28, 10), (False, True): (60, 68, 16), (True, False): (84, 92, 22), (True, True): (96, 104, 25)}[(coord, depth)]
+            alg = R * (A + 4) + W * H * I + 8 * tiles + 4 * G * Pv
+            dur = tot / n * 1e-3
+            roofline = {"kernel": "render_backward_kernel", "bound": "hbm", "achieved": alg / dur / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / dur / 1e9 / peak, "traffic": None, "algorithmic_bytes": alg, "avg_launch_ms": tot / n,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                        "note": "kernel is FP32-issue bound (about 0.5 G pixel-splat pair gradients per launch), see DESIGN.md"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world if multi else 1, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": a.impl,
+            "config": {"workload": f"{a.config}: {P} random-init Gaussians (SURVEY app. C seed 1234), {W}x{H}, SH deg 3, "
+                                   f"require_depth={depth} require_coord={coord}, fwd+bwd at the _C boundary, num_rendered={R if not multi else 'per-slab'}",
+                       "parallelism": f"tile-row slabs x{world}" if multi else "single GPU",
+                       "l2": "per-step working set (192 MB SH + 248 MB SH grads + 64 MB records + sort buffers) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps,
+                    "api": "GaussianRasterizer autograd module + L1/depth/normal loss, GT maps H2D from pinned memory on a side stream"},
+            "gpu_launches": launches, "clocks": clk.summary(),
+        }
+        if stages:
+            line["stage_ms"] = {k: v[0] / max(v[1], 1) for k, v in stages.items()}
+        if roofline:
+            line["roofline"] = roofline
+        if a.impl == "reference":
+            line["cpu_baseline"] = {"value": value, "unit": "Mpix/s", "cores": 0, "kind": "reference",
+                                    "sample": "reference CUDA rasterizer (oracle/_ref, sm_100a build of /root/reference) on 1xB200; the reference has no CPU rasterizer"}
+            line["e2e"] = {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+        elif not a.no_cpu_baseline and not multi:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if multi:
+        dist.destroy_process_group()
+
+
+def last_radii(C, sc, coord, depth):
+    from rade_gs_b200 import rawapi
+    return rawapi.forward(C, sc, coord, depth)["radii"]
+
+
+if __name__ == "__main__":
+    main()

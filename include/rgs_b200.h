@@ -172,6 +172,12 @@ typedef struct rgs_debug_views {
 int32_t rgs_debug_get_views(const rgs_camera* cam, int32_t P, int64_t num_rendered, const char* geom_buffer,
                             const char* binning_buffer, const char* image_buffer, rgs_debug_views* views);
 
+/* Optional per-stage device timing for benchmarking: while enabled, every stage launch is bracketed by CUDA
+ * events on the launching stream.  rgs_stage_times synchronises on them and returns, per stage, the summed
+ * duration and the number of launches since timing was switched on (names are static strings). */
+void rgs_stage_timing(int32_t enable);
+int32_t rgs_stage_times(const char** names, double* total_ms, int64_t* launches, int32_t capacity);
+
 const char* rgs_last_error(void);
 int32_t rgs_abi_version(void);
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "rgs_common.cuh"
 
@@ -17,6 +18,37 @@ static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static thread_local std::string t_error;
+
+// ---- optional per-stage device timing (bench.py's roofline leg): cudaEvents recorded on the launching stream
+// around each stage, read back by rgs_stage_times() after a synchronize.  Off by default: zero overhead.
+enum Stage { ST_PREPROCESS, ST_SCAN, ST_BINNING, ST_RENDER_FWD, ST_RENDER_BWD, ST_PREPROCESS_BWD, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"preprocess_forward", "scan", "binning_sort", "render_forward", "render_backward", "preprocess_backward"};
+struct StageRec { int stage; cudaEvent_t a, b; };
+static std::mutex g_stage_mu;
+static std::vector<StageRec> g_stage_pending;
+static double g_stage_ms[ST_COUNT];
+static int64_t g_stage_n[ST_COUNT];
+static std::atomic<int> g_stage_on{0};
+
+struct StageScope {
+	cudaStream_t s; int stage; cudaEvent_t a = nullptr, b = nullptr; bool on;
+	StageScope(int st, cudaStream_t stream) : s(stream), stage(st), on(g_stage_on.load() != 0) {
+		if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+	}
+	~StageScope() {
+		if (on) { cudaEventRecord(b, s); std::lock_guard<std::mutex> lk(g_stage_mu); g_stage_pending.push_back({stage, a, b}); }
+	}
+};
+static void stage_collect() {
+	std::lock_guard<std::mutex> lk(g_stage_mu);
+	for (auto& r : g_stage_pending) {
+		cudaEventSynchronize(r.b);
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { g_stage_ms[r.stage] += ms; g_stage_n[r.stage]++; }
+		cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+	}
+	g_stage_pending.clear();
+}
 
 static int fail(int code, const std::string& msg) {
 	t_error = msg;
@@ -141,6 +173,17 @@ extern "C" {
 const char* rgs_last_error(void) { return t_error.c_str(); }
 int32_t rgs_abi_version(void) { return RGS_ABI_VERSION; }
 int64_t rgs_launch_count(void) { return g_launches.load(); }
+void rgs_stage_timing(int32_t enable) {
+	stage_collect();
+	if (enable) { std::lock_guard<std::mutex> lk(g_stage_mu); for (int i = 0; i < ST_COUNT; i++) { g_stage_ms[i] = 0; g_stage_n[i] = 0; } }
+	g_stage_on.store(enable ? 1 : 0);
+}
+int32_t rgs_stage_times(const char** names, double* total_ms, int64_t* launches, int32_t capacity) {
+	stage_collect();
+	int n = capacity < ST_COUNT ? capacity : ST_COUNT;
+	for (int i = 0; i < n; i++) { names[i] = kStageNames[i]; total_ms[i] = g_stage_ms[i]; launches[i] = g_stage_n[i]; }
+	return n;
+}
 int32_t rgs_grad_stride(int32_t require_coord, int32_t /*require_depth*/) { return grad_floats(require_coord != 0); }
 
 int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_forward_out* out, const rgs_buffers* bufs, void* cuda_stream) {
@@ -170,9 +213,9 @@ int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_fo
 
 	int64_t R = 0;
 	if (P > 0) {
-		launch_preprocess_forward(p, g, out->radii, s);
+		{ StageScope sc(ST_PREPROCESS, s); launch_preprocess_forward(p, g, out->radii, s); }
 		if ((rc = debug_sync(cam, s, "preprocess")) != RGS_OK) return rc;
-		launch_scan(g, P, s);
+		{ StageScope sc(ST_SCAN, s); launch_scan(g, P, s); }
 		// the one host sync of the forward pass: instance count sizes the binning buffers and is returned to the
 		// caller (reference: blocking cudaMemcpy, rasterizer_impl.cu:354)
 		uint32_t* box = pinned_mailbox();
@@ -188,9 +231,9 @@ int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_fo
 	if (!bin_ptr) return fail(RGS_E_ALLOC, "binning buffer callback returned NULL");
 	BinView b = carve_bin(bin_ptr, (size_t)R, sort_bytes, nullptr);
 
-	launch_binning(p, g, b, img, out->radii, R, s);
+	{ StageScope sc(ST_BINNING, s); launch_binning(p, g, b, img, out->radii, R, s); }
 	if ((rc = debug_sync(cam, s, "binning")) != RGS_OK) return rc;
-	launch_render_forward(p, g, b, img, ro, s);
+	{ StageScope sc(ST_RENDER_FWD, s); launch_render_forward(p, g, b, img, ro, s); }
 	if ((rc = debug_sync(cam, s, "render")) != RGS_OK) return rc;
 	return R;
 }
@@ -220,7 +263,7 @@ int32_t rgs_backward_render(const rgs_camera* cam, const rgs_gaussians* gs, cons
 	cudaStream_t s = (cudaStream_t)cuda_stream;
 	RenderGradIn gin{in->dL_dout_color, in->dL_dout_coord, in->dL_dout_mcoord, in->dL_dout_depth, in->dL_dout_mdepth,
 	                 in->dL_dout_alpha, in->dL_dout_normal, in->out_alpha, in->out_normal};
-	launch_render_backward(p, g, b, img, gin, grad_accum, s);
+	{ StageScope sc(ST_RENDER_BWD, s); launch_render_backward(p, g, b, img, gin, grad_accum, s); }
 	return debug_sync(cam, s, "backward render");
 }
 
@@ -236,7 +279,7 @@ int32_t rgs_backward_preprocess(const rgs_camera* cam, const rgs_gaussians* gs, 
 	if (!grad_accum || !out) return fail(RGS_E_INVALID, "null gradient accumulator / outputs");
 	cudaStream_t s = (cudaStream_t)cuda_stream;
 	ParamGradOut po{out->dL_dmeans2D, out->dL_dcolors, out->dL_dopacity, out->dL_dmeans3D, out->dL_dcov3D, out->dL_dsh, out->dL_dscales, out->dL_drotations};
-	launch_preprocess_backward(p, g, in->radii, grad_accum, po, s);
+	{ StageScope sc(ST_PREPROCESS_BWD, s); launch_preprocess_backward(p, g, in->radii, grad_accum, po, s); }
 	return debug_sync(cam, s, "backward preprocess");
 }
 

@@ -6,10 +6,8 @@
 //
 // What is different from the reference (by design, results within tolerance; keys bit-exact):
 //   * one packed 64/96-byte render record per Gaussian instead of nine SoA arrays;
-//   * the 3x3 symmetric eigen-decomposition of Sigma (forward.cu:135-155) is not iterated when Sigma
-//     comes from (scale, unit quaternion): Sigma = R S^2 R^T already IS its eigen-decomposition, so
-//     Sigma^-1 in camera space is A diag(1/s^2) A^T with A = R_view * R.  A Jacobi solver covers
-//     cov3D_precomp and non-unit quaternions;
+//   * the 3x3 symmetric eigen-decomposition of Sigma keeps the reference's algorithm and absolute stopping
+//     tests (rgs_geom.cuh explains why a more accurate one would break parity of the normal map);
 //   * the key-determining chain (p_view.z, NDC->pixel, cov2D -> radius -> tile rect) keeps the
 //     reference's expression shapes so both builds round identically.
 #include <math_constants.h>
@@ -87,25 +85,18 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
 
 		// ---- 3D covariance (forward.cu:270-304) ----
 		float cov3D[6];
-		M3 Rg;
-		V3 s_mod = {0.f, 0.f, 0.f};
-		bool analytic = false;
 		if (p.cov3D_precomp != nullptr) {
 #pragma unroll
 			for (int i = 0; i < 6; i++) cov3D[i] = p.cov3D_precomp[6 * idx + i];
-			Rg = m3(1, 0, 0, 0, 1, 0, 0, 0, 1);
 		} else {
 			const float sx = p.scales[3 * idx], sy = p.scales[3 * idx + 1], sz = p.scales[3 * idx + 2];
 			const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * idx);
-			s_mod = V3{p.scale_modifier * sx, p.scale_modifier * sy, p.scale_modifier * sz};
-			M3 S = m3(s_mod.x, 0.f, 0.f, 0.f, s_mod.y, 0.f, 0.f, 0.f, s_mod.z);
-			Rg = quat_to_glm_rot(q.x, q.y, q.z, q.w);
+			M3 S = m3(p.scale_modifier * sx, 0.f, 0.f, 0.f, p.scale_modifier * sy, 0.f, 0.f, 0.f, p.scale_modifier * sz);
+			const M3 Rg = quat_to_glm_rot(q.x, q.y, q.z, q.w);
 			M3 Mm = S * Rg;
 			M3 Sigma = transpose(Mm) * Mm;
 			cov3D[0] = Sigma.c[0].x; cov3D[1] = Sigma.c[0].y; cov3D[2] = Sigma.c[0].z;
 			cov3D[3] = Sigma.c[1].y; cov3D[4] = Sigma.c[1].z; cov3D[5] = Sigma.c[2].z;
-			const float qn = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
-			analytic = fabsf(qn - 1.0f) < 1e-4f;
 		}
 
 		// ---- EWA 2D covariance (forward.cu:85-124); this chain decides the radius ----
@@ -154,16 +145,12 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
 				float2 ray_plane = {0.f, 0.f};
 				float3 normal = {0.f, 0.f, 0.f};
 				if (p.coord || p.depth) {
-					float lam[3];
-					M3 E;
-					sigma_eigen(analytic, Rg, s_mod, cov3D, lam, E);
-					bool well;
-					int min_id;
+					const SigmaInv si = sigma_inverse(cov3D);
+					const M3 cov_cam_inv = transpose(Wm) * si.inv * Wm;
 					const V3 uvh = {txtz, tytz, 1.f};
-					const V3 uvh_m = apply_cov_cam_inv(E, lam, V, uvh, well, min_id);
-					const float inv_len = 1.0f / sqrtf(dot3(uvh_m, uvh_m));
-					const V3 uvh_mn = uvh_m * inv_len;
-					if (!isnan(uvh_mn.x)) {
+					const V3 uvh_m = mulcol(cov_cam_inv, uvh);
+					const V3 uvh_mn = uvh_m * (1.0f / sqrtf(dot3(uvh_m, uvh_m)));
+					if (!isnan(uvh_mn.x) && si.solved) {
 						const float u2 = txtz * txtz, v2 = tytz * tytz, uv = txtz * tytz;
 						const float l = sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
 						const float vbn = dot3(uvh_mn, uvh);
@@ -180,8 +167,9 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
 						cam_plane[5] = (t.y + plane1 * t.z) / nl / p.focal_y;
 						ray_plane = {plane0 * l / nl / p.focal_x, plane1 * l / nl / p.focal_y};
 						const V3 rn = {-plane0 * factor_normal, -plane1 * factor_normal, -1.f};
-						const V3 cn = {rn.x / t.z + rn.z * (t.x / l), rn.y / t.z + rn.z * (t.y / l),
-						               (-(t.x) / (t.z * t.z)) * rn.x + (-(t.y) / (t.z * t.z)) * rn.y + (t.z / l) * rn.z};
+						// nJ * rn with nJ columns (1/tz, 0, -tx/tz^2), (0, 1/tz, -ty/tz^2), (tx/l, ty/l, tz/l)  (forward.cu:176-179,257)
+						const M3 nJ = m3(1 / t.z, 0.0f, -(t.x) / (t.z * t.z), 0.0f, 1 / t.z, -(t.y) / (t.z * t.z), t.x / l, t.y / l, t.z / l);
+						const V3 cn = mulcol(nJ, rn);
 						const float cinv = 1.0f / sqrtf(dot3(cn, cn));
 						normal = {cn.x * cinv, cn.y * cinv, cn.z * cinv};
 					}

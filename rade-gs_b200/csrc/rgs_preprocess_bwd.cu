@@ -12,33 +12,10 @@
 //     (rasterizer_impl.cu:569 vs backward.h:94), so `combined_opacity` below is dL_dconic.w.  Set
 //     RGS_FIX_MIP_GRADIENT to use the true opacity*coef instead (off by default: parity first);
 //   * gradients are w.r.t. the quaternion as given (no normalisation inside, backward.cu:554);
-//   * Sigma's eigen-decomposition is analytic for (scale, unit quaternion) inputs, Jacobi otherwise
-//     (see rgs_preprocess.cu).
+//   * Sigma's eigen-decomposition follows the reference's solver and stopping rules (see rgs_geom.cuh).
 #include "rgs_geom.cuh"
 
 namespace rgs {
-
-namespace {
-
-// y = Sigma^-1-like operator in WORLD space applied to x: E diag(1/lam) E^T x, or e_min (e_min . x).
-__device__ __forceinline__ V3 apply_world_inv(const M3& E, const float lam[3], bool well, int min_id, V3 x) {
-	if (well) {
-		const float w0 = dot3(E.c[0], x) / lam[0], w1 = dot3(E.c[1], x) / lam[1], w2 = dot3(E.c[2], x) / lam[2];
-		return V3{E.c[0].x * w0 + E.c[1].x * w1 + E.c[2].x * w2, E.c[0].y * w0 + E.c[1].y * w1 + E.c[2].y * w2,
-		          E.c[0].z * w0 + E.c[1].z * w1 + E.c[2].z * w2};
-	}
-	const V3 e = min_id == 0 ? E.c[0] : (min_id == 1 ? E.c[1] : E.c[2]);
-	return e * dot3(e, x);
-}
-// Rv * x  and  Rv^T * x  for the rotation part of the view matrix (Rv[i][j] = V[i + 4 j])
-__device__ __forceinline__ V3 rot_view(const float* V, V3 x) {
-	return V3{V[0] * x.x + V[4] * x.y + V[8] * x.z, V[1] * x.x + V[5] * x.y + V[9] * x.z, V[2] * x.x + V[6] * x.y + V[10] * x.z};
-}
-__device__ __forceinline__ V3 rot_view_T(const float* V, V3 x) {
-	return V3{V[0] * x.x + V[1] * x.y + V[2] * x.z, V[4] * x.x + V[5] * x.y + V[6] * x.z, V[8] * x.x + V[9] * x.y + V[10] * x.z};
-}
-
-}  // namespace
 
 __global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, GeomView g, const int* __restrict__ radii,
                                                                    const float* __restrict__ grad_accum, ParamGradOut out, int fix_mip) {
@@ -99,7 +76,6 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, G
 		M3 Rg = m3(1, 0, 0, 0, 1, 0, 0, 0, 1);
 		V3 s_mod = {0, 0, 0};
 		float4 q = {1, 0, 0, 0};
-		bool analytic = false;
 		const bool from_scales = (p.cov3D_precomp == nullptr);
 		if (!from_scales) {
 #pragma unroll
@@ -113,8 +89,6 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, G
 			M3 Sigma = transpose(Mm) * Mm;
 			cov3D[0] = Sigma.c[0].x; cov3D[1] = Sigma.c[0].y; cov3D[2] = Sigma.c[0].z;
 			cov3D[3] = Sigma.c[1].y; cov3D[4] = Sigma.c[1].z; cov3D[5] = Sigma.c[2].z;
-			const float qn = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
-			analytic = fabsf(qn - 1.0f) < 1e-4f;
 		}
 
 		float3 t = xform4x3(mean, V);
@@ -144,91 +118,86 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, G
 		float plane0 = 0.f, plane1 = 0.f, dL_du = 0.f, dL_dv = 0.f, dL_dl = 0.f, l = 1.f, nl = 1.f;
 		V3 dcn = {0, 0, 0}, rn = {0, 0, 0};  // dL_dnJ = dcn * rn^T
 		if (p.coord || p.depth) {
-			float lam[3];
-			M3 E;
-			if (analytic) {
-				lam[0] = s_mod.x * s_mod.x; lam[1] = s_mod.y * s_mod.y; lam[2] = s_mod.z * s_mod.z;
-				E = transpose(Rg);
-			} else {
-				eig_sym3_jacobi(cov3D, lam, E);
-			}
-			const int min_id = lam[0] > lam[1] ? (lam[1] > lam[2] ? 2 : 1) : (lam[0] > lam[2] ? 2 : 0);
-			const bool well = lam[min_id] > 0.00000001f;
+			const SigmaInv si = sigma_inverse(cov3D);
+			const M3& Vrk_inv = si.inv;
+			const M3 cov_cam_inv = transpose(Wm) * Vrk_inv * Wm;
 			const V3 uvh = {txtz, tytz, 1.f};
-			const V3 W_uvh = rot_view_T(V, uvh);                                   // W * uvh (world)
-			const V3 uvh_m = rot_view(V, apply_world_inv(E, lam, well, min_id, W_uvh));  // cov_cam_inv * uvh
+			const V3 uvh_m = mulcol(cov_cam_inv, uvh);
 			const V3 uvh_mn = uvh_m * (1.0f / sqrtf(dot3(uvh_m, uvh_m)));
-			if (!isnan(uvh_mn.x)) {
+			if (!isnan(uvh_mn.x) && si.solved) {
 				const float vb = dot3(uvh_m, uvh);
 				const float vbn = dot3(uvh_mn, uvh);
 				l = sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+				const M3 nJ = m3(1 / t.z, 0.0f, -(t.x) / (t.z * t.z), 0.0f, 1 / t.z, -(t.y) / (t.z * t.z), t.x / l, t.y / l, t.z / l);
+				const M3 nJ_inv = m3(v2 + 1, -uv, 0.f, -uv, u2 + 1, 0.f, -txtz, -tytz, 0.f);
 				const float clamp_vb = max(vb, 0.0000001f);
 				const float clamp_vbn = max(vbn, 0.0000001f);
 				nl = u2 + v2 + 1;
 				const float factor_normal = l / nl;
 				const V3 qv = uvh_mn / clamp_vbn;  // uvh_m_vb
-				plane0 = (v2 + 1) * qv.x + (-uv) * qv.y + (-txtz) * qv.z;
-				plane1 = (-uv) * qv.x + (u2 + 1) * qv.y + (-tytz) * qv.z;
+				const V3 plane = mulcol(nJ_inv, qv);
+				plane0 = plane.x;
+				plane1 = plane.y;
 				const float2 cp0 = {(-(v2 + 1) * t.z + plane0 * t.x) / nl, (uv * t.z + plane1 * t.x) / nl};
 				const float2 cp1 = {(uv * t.z + plane0 * t.y) / nl, (-(u2 + 1) * t.z + plane1 * t.y) / nl};
 				const float2 cp2 = {(t.x + plane0 * t.z) / nl, (t.y + plane1 * t.z) / nl};
 				const float2 ray_plane = {plane0 * factor_normal, plane1 * factor_normal};
 				rn = V3{-plane0 * factor_normal, -plane1 * factor_normal, -1.f};
-				// nJ rows: (1/tz, 0, tx/l), (0, 1/tz, ty/l), (-tx/tz^2, -ty/tz^2, tz/l)
-				const V3 cn = {rn.x / t.z + rn.z * (t.x / l), rn.y / t.z + rn.z * (t.y / l),
-				               (-(t.x) / (t.z * t.z)) * rn.x + (-(t.y) / (t.z * t.z)) * rn.y + (t.z / l) * rn.z};
+				const V3 cn = mulcol(nJ, rn);
+				const V3 nvec = cn * (1.0f / sqrtf(dot3(cn, cn)));
 				const float lv = sqrtf(dot3(cn, cn));
-				const V3 nvec = cn * (1.0f / lv);
 				const V3 dn_lv = dL_dnormal / lv;
 				dcn = dn_lv - nvec * dot3(nvec, dn_lv);
-				// transpose(nJ) * dcn
-				const V3 drn = {dcn.x / t.z + (-(t.x) / (t.z * t.z)) * dcn.z, dcn.y / t.z + (-(t.y) / (t.z * t.z)) * dcn.z,
-				                (t.x / l) * dcn.x + (t.y / l) * dcn.y + (t.z / l) * dcn.z};
+				const V3 drn = mulcol(transpose(nJ), dcn);
 				dL_dl = (-plane0 * drn.x - plane1 * drn.y + plane0 * dray.x + plane1 * dray.y) / nl;
 				const float dpx = (t.x * dcp0.x + t.y * dcp1.x + t.z * dcp2.x - l * drn.x + dray.x * l) / nl;
 				const float dpy = (t.x * dcp0.y + t.y * dcp1.y + t.z * dcp2.y - l * drn.y + dray.y * l) / nl;
+				const V3 dp3 = {dpx, dpy, 0.f};
 				const float dL_dnl = (-dcp0.x * cp0.x - dcp0.y * cp0.y - dcp1.x * cp1.x - dcp1.y * cp1.y - dcp2.x * cp2.x - dcp2.y * cp2.y -
 				                      drn.x * rn.x - drn.y * rn.y - dray.x * ray_plane.x - dray.y * ray_plane.y) / nl;
 				const float tmp = dpx * plane0 + dpy * plane1;
-				// transpose(nJ_inv) * (dpx, dpy, 0)
-				const V3 njt_dp = {(v2 + 1) * dpx + (-uv) * dpy, (-uv) * dpx + (u2 + 1) * dpy, (-txtz) * dpx + (-tytz) * dpy};
-				const V3 W_njt = rot_view_T(V, njt_dp);
-				if (well) {
-					// dL_dVrk = -(Sinv w)(Sinv/vb (w*(-tmp) + W njt))^T
-					const V3 a = apply_world_inv(E, lam, true, min_id, W_uvh);
-					const V3 rhs = W_uvh * (-tmp) + W_njt;
-					const V3 b = apply_world_inv(E, lam, true, min_id, rhs) / clamp_vb;
-					dVrk[0] = -(a.x * b.x);
-					dVrk[3] = -(a.y * b.y);
-					dVrk[5] = -(a.z * b.z);
-					dVrk[1] = -(a.x * b.y) - (a.y * b.x);
-					dVrk[2] = -(a.x * b.z) - (a.z * b.x);
-					dVrk[4] = -(a.y * b.z) - (a.z * b.y);
+				const V3 W_uvh = mulcol(Wm, uvh);
+				const M3 nJ_inv_T = transpose(nJ_inv);
+				M3 dL_dVrk = m3(0, 0, 0, 0, 0, 0, 0, 0, 0);
+				if (si.well) {
+					// -outer(Vrk_inv W uvh, (Vrk_inv / vb) (W uvh (-tmp) + W nJ_inv^T dplane))      (backward.cu:334)
+					M3 Vs;
+					Vs.c[0] = Vrk_inv.c[0] / clamp_vb; Vs.c[1] = Vrk_inv.c[1] / clamp_vb; Vs.c[2] = Vrk_inv.c[2] / clamp_vb;
+					const V3 rhs = W_uvh * (-tmp) + mulcol(Wm * nJ_inv_T, dp3);
+					const M3 o = outer(mulcol(Vrk_inv, W_uvh), mulcol(Vs, rhs));
+					dL_dVrk.c[0] = V3{-o.c[0].x, -o.c[0].y, -o.c[0].z};
+					dL_dVrk.c[1] = V3{-o.c[1].x, -o.c[1].y, -o.c[1].z};
+					dL_dVrk.c[2] = V3{-o.c[2].x, -o.c[2].y, -o.c[2].z};
 				} else {
+					// rank-1 branch: through the smallest eigenvector (backward.cu:336-350)
 					const float dL_dvb = -tmp / clamp_vb;
-					const V3 c = W_uvh * dL_dvb + rot_view_T(V, njt_dp / clamp_vb);
-					const V3 emin = min_id == 0 ? E.c[0] : (min_id == 1 ? E.c[1] : E.c[2]);
-					// (w c^T + c w^T) e_min
-					const V3 dLdv = W_uvh * dot3(c, emin) + c * dot3(W_uvh, emin);
+					const V3 nji = mulcol(nJ_inv_T, V3{dpx / clamp_vb, dpy / clamp_vb, 0.f});
+					const M3 dVi = outer(W_uvh, W_uvh * dL_dvb + mulcol(Wm, nji));
+					const M3 dViT = transpose(dVi);
+					M3 sym;
+					sym.c[0] = dVi.c[0] + dViT.c[0]; sym.c[1] = dVi.c[1] + dViT.c[1]; sym.c[2] = dVi.c[2] + dViT.c[2];
+					const V3 emin = si.E.c[si.min_id];
+					const V3 dLdv = mulcol(sym, emin);
 #pragma unroll
 					for (int j = 0; j < 3; j++) {
-						if (j != min_id) {
-							const V3 ej = E.c[j];
-							const float scale = dot3(ej, dLdv) / min(lam[min_id] - lam[j], -0.0000001f);
-							const V3 a = ej * scale;  // outer(a, emin)
-							dVrk[0] += a.x * emin.x;
-							dVrk[3] += a.y * emin.y;
-							dVrk[5] += a.z * emin.z;
-							dVrk[1] += a.x * emin.y + a.y * emin.x;
-							dVrk[2] += a.x * emin.z + a.z * emin.x;
-							dVrk[4] += a.y * emin.z + a.z * emin.y;
+						if (j != si.min_id) {
+							const float scale = dot3(si.E.c[j], dLdv) / min(si.lam[si.min_id] - si.lam[j], -0.0000001f);
+							const M3 o = outer(si.E.c[j] * scale, emin);
+							dL_dVrk.c[0] = dL_dVrk.c[0] + o.c[0]; dL_dVrk.c[1] = dL_dVrk.c[1] + o.c[1]; dL_dVrk.c[2] = dL_dVrk.c[2] + o.c[2];
 						}
 					}
 				}
-				// dL_duvh = 2(-tmp) q + cov_cam_inv/vb * njt_dp
-				const V3 cci = rot_view(V, apply_world_inv(E, lam, well, min_id, W_njt)) / clamp_vb;
-				const V3 dL_duvh = qv * (2 * (-tmp)) + cci;
-				// dL_dnJ_inv = (dpx,dpy,0) q^T
+				dVrk[0] = at(dL_dVrk, 0, 0);
+				dVrk[3] = at(dL_dVrk, 1, 1);
+				dVrk[5] = at(dL_dVrk, 2, 2);
+				dVrk[1] = at(dL_dVrk, 0, 1) + at(dL_dVrk, 1, 0);
+				dVrk[2] = at(dL_dVrk, 0, 2) + at(dL_dVrk, 2, 0);
+				dVrk[4] = at(dL_dVrk, 1, 2) + at(dL_dVrk, 2, 1);
+				// dL_duvh = 2(-tmp) q + (cov_cam_inv / vb) nJ_inv^T dplane      (backward.cu:353)
+				M3 Cs;
+				Cs.c[0] = cov_cam_inv.c[0] / clamp_vb; Cs.c[1] = cov_cam_inv.c[1] / clamp_vb; Cs.c[2] = cov_cam_inv.c[2] / clamp_vb;
+				const V3 dL_duvh = qv * (2 * (-tmp)) + mulcol(Cs * nJ_inv_T, dp3);
+				// dL_dnJ_inv = outer(dplane, q): [c][r] = dp_r q_c
 				const float nji01 = dpy * qv.x, nji10 = dpx * qv.y, nji11 = dpy * qv.y, nji00 = dpx * qv.x, nji20 = dpx * qv.z, nji21 = dpy * qv.z;
 				dL_du = dL_dnl * 2 * txtz + dL_duvh.x + (nji01 + nji10) * (-tytz) + 2 * nji11 * txtz - nji20 +
 				        (dcp0.y * t.y + dcp1.x * t.y + dcp1.y * (-2 * t.x)) / nl;

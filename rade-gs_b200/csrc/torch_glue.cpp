@@ -381,4 +381,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("grad_stride", [](bool require_coord, bool require_depth) { return rgs_grad_stride(require_coord, require_depth); });
 	m.def("launch_count", []() { return rgs_launch_count(); });
 	m.def("abi_version", []() { return rgs_abi_version(); });
+	m.def("stage_timing", [](bool on) { rgs_stage_timing(on); });
+	m.def("stage_times", []() {
+		const char* names[16]; double ms[16]; int64_t n[16];
+		const int k = rgs_stage_times(names, ms, n, 16);
+		py::dict d;
+		for (int i = 0; i < k; i++) d[names[i]] = py::make_tuple(ms[i], n[i]);
+		return d;
+	});
 }

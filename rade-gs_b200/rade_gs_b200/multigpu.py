@@ -1,0 +1,156 @@
+"""Tile-row sharding of one camera across the GPUs of a box (the reference is single-GPU only).
+
+Every rank holds the full Gaussian set and runs preprocess on all of it (identical on every rank); rank r bins,
+sorts and blends only the tile rows of its slab, so the union of the per-rank sorted lists is the reference's
+list.  Backward has exactly one exchange step: the packed screen-space gradient rows written by
+backward-render are plain sums over pixels, hence additive across slabs -- they are summed with ONE all-reduce
+(NCCL over NVLink on GPUs, gloo in the CPU tests) and only then turned into parameter gradients.  The reduce
+has to sit before backward-preprocess, not after it: with kernel_size > 0 that stage multiplies two
+accumulated quantities (the reference's mip-gradient aliasing), so per-slab results would not
+add up to the single-GPU answer.
+
+`backward_two_stage` is written against three callables so that the same control flow is exercised on CPU
+(gloo + the oracle) and on GPUs (NCCL + the CUDA stages).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+TILE = 16
+
+
+def tile_rows(height: int) -> int:
+    return (height + TILE - 1) // TILE
+
+
+def partition_tile_rows(grid_y: int, world_size: int, weights: Sequence[float] | None = None) -> List[Tuple[int, int]]:
+    """Contiguous [begin, end) tile-row slabs, one per rank.
+
+    Without weights rows are split as evenly as possible (earlier ranks take the remainder, e.g. 68 rows over 8
+    ranks -> 9,9,9,9,8,8,8,8).  With per-row weights (e.g. instances per tile row from a previous frame) the cut
+    points equalise the weight prefix sums; every rank still gets a (possibly empty) contiguous range and the
+    ranges tile [0, grid_y) exactly.
+    """
+    if world_size <= 0:
+        raise ValueError("world_size must be positive")
+    if weights is None:
+        base, rem = divmod(grid_y, world_size)
+        out, b = [], 0
+        for r in range(world_size):
+            e = b + base + (1 if r < rem else 0)
+            out.append((b, e))
+            b = e
+        return out
+    if len(weights) != grid_y:
+        raise ValueError("need one weight per tile row")
+    total = float(sum(weights))
+    if total <= 0:
+        return partition_tile_rows(grid_y, world_size)
+    cuts, acc, r = [0], 0.0, 1
+    for y, w in enumerate(weights):
+        acc += float(w)
+        while r < world_size and acc >= total * r / world_size:
+            cuts.append(y + 1)
+            r += 1
+    while len(cuts) < world_size:
+        cuts.append(grid_y)
+    cuts.append(grid_y)
+    return [(cuts[i], max(cuts[i], cuts[i + 1])) for i in range(world_size)]
+
+
+def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place sum over ranks; a no-op outside an initialised process group (single-GPU path)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def backward_two_stage(stage1_render: Callable[[], torch.Tensor], stage2_preprocess: Callable[[torch.Tensor], tuple], group=None):
+    """slab-local scatter -> one all-reduce -> replicated parameter gradients."""
+    acc = stage1_render()
+    allreduce_sum_(acc, group)
+    return stage2_preprocess(acc)
+
+
+class _ShardedRasterize(torch.autograd.Function):
+    """Autograd node of the row-sharded rasterizer; same argument / gradient order as the single-GPU
+    `_RasterizeGaussians` (reference: diff_gaussian_rasterization/__init__.py:44-169)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, slab, group):
+        from diff_gaussian_rasterization import _C
+        s = raster_settings
+        out = _C.rasterize_gaussians_slab(
+            s.bg, means3D, colors_precomp, opacities, scales, rotations, s.scale_modifier, cov3Ds_precomp, s.viewmatrix, s.projmatrix,
+            s.tanfovx, s.tanfovy, s.kernel_size, s.image_height, s.image_width, sh, s.sh_degree, s.campos, s.prefiltered,
+            s.require_coord, s.require_depth, s.debug, slab[0], slab[1])
+        num_rendered, color, coord, mcoord, alpha, normal, depth, mdepth, radii, geom, binning, img = out
+        ctx.s, ctx.slab, ctx.group, ctx.num_rendered = s, slab, group, num_rendered
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, normal, radii, sh, geom, binning, img, alpha, opacities)
+        return color, radii, coord, mcoord, depth, mdepth, alpha, normal
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_coord, g_mcoord, g_depth, g_mdepth, g_alpha, g_normal):
+        from diff_gaussian_rasterization import _C
+        s = ctx.s
+        colors_precomp, means3D, scales, rotations, cov3Ds_precomp, normal, radii, sh, geom, binning, img, alpha, opacities = ctx.saved_tensors
+
+        def stage1():
+            return _C.rasterize_gaussians_backward_render(
+                s.bg, means3D, radii, colors_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp, s.viewmatrix, s.projmatrix,
+                s.tanfovx, s.tanfovy, s.kernel_size, g_color, g_coord, g_mcoord, g_depth, g_mdepth, g_alpha, g_normal, normal, sh,
+                s.sh_degree, s.campos, geom, ctx.num_rendered, binning, img, alpha, s.require_coord, s.require_depth, s.debug,
+                ctx.slab[0], ctx.slab[1])
+
+        def stage2(acc):
+            return _C.rasterize_gaussians_backward_preprocess(
+                acc, s.bg, means3D, radii, colors_precomp, opacities, scales, rotations, s.scale_modifier, cov3Ds_precomp, s.viewmatrix,
+                s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size, s.image_height, s.image_width, sh, s.sh_degree, s.campos, geom,
+                s.require_coord, s.require_depth, s.debug)
+
+        g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = backward_two_stage(stage1, stage2, ctx.group)
+        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, None, None, None
+
+
+class ShardedGaussianRasterizer(torch.nn.Module):
+    """`GaussianRasterizer` whose work is split by tile rows over the ranks of a process group.
+
+    Each rank returns full-size maps of which only its slab rows are filled (the rest is zero); callers that need
+    the whole image sum or gather the slabs (`gather_image`).  Gradients returned on every rank are the full,
+    already-reduced parameter gradients.
+    """
+
+    def __init__(self, raster_settings, rank: int | None = None, world_size: int | None = None, group=None, row_weights=None):
+        super().__init__()
+        self.raster_settings = raster_settings
+        self.group = group
+        if world_size is None:
+            world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rank, self.world_size = rank, world_size
+        self.slabs = partition_tile_rows(tile_rows(raster_settings.image_height), world_size, row_weights)
+        self.slab = self.slabs[rank]
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None):
+        from diff_gaussian_rasterization import _absent, _check_exclusive
+        _check_exclusive(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        shs = _absent() if shs is None else shs
+        colors_precomp = _absent() if colors_precomp is None else colors_precomp
+        scales = _absent() if scales is None else scales
+        rotations = _absent() if rotations is None else rotations
+        cov3D_precomp = _absent() if cov3D_precomp is None else cov3D_precomp
+        return _ShardedRasterize.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                       self.raster_settings, self.slab, self.group)
+
+    def pixel_rows(self) -> Tuple[int, int]:
+        H = self.raster_settings.image_height
+        return min(self.slab[0] * TILE, H), min(self.slab[1] * TILE, H)
+
+    def gather_image(self, img: torch.Tensor) -> torch.Tensor:
+        """Sum of the slab images = the whole image (rows outside a rank's slab are zero)."""
+        out = img.clone()
+        return allreduce_sum_(out, self.group)

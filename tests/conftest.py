@@ -1,0 +1,48 @@
+"""Shared test plumbing.  `-m "not gpu"` runs here on CPU; `-m gpu` runs on the B200 box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "rade-gs_b200"), os.path.join(ROOT, "oracle"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz")) if os.path.isdir(GOLDEN_DIR) else []
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+
+
+def golden_oracle_inputs(d):
+    """oracle.Inputs for a golden fixture."""
+    import oracle
+    kw = {}
+    if "in_colors_precomp" in d:
+        kw["colors_precomp"] = d["in_colors_precomp"]
+    else:
+        kw["shs"] = d["in_shs"]
+    if "in_cov3D_precomp" in d:
+        kw["cov3D_precomp"] = d["in_cov3D_precomp"]
+    else:
+        kw["scales"], kw["rotations"] = d["in_scales"], d["in_rotations"]
+    return oracle.Inputs(d["in_means3D"], d["in_opacities"], d["in_viewmatrix"], d["in_projmatrix"], d["in_campos"], d["in_bg"],
+                         int(d["meta_W"]), int(d["meta_H"]), float(d["in_tanfov"][0]), float(d["in_tanfov"][1]), sh_degree=int(d["meta_deg"]),
+                         kernel_size=float(d["meta_ks"]), require_coord=bool(d["meta_coord"]), require_depth=bool(d["meta_depth"]), **kw)
+
+
+def golden_upstream(d):
+    return {k: d["gin_" + k] for k in ("color", "coord", "mcoord", "depth", "mdepth", "alpha", "normal")}
+
+
+@pytest.fixture(params=GOLDEN_CASES)
+def golden(request):
+    return request.param, load_golden(request.param)

@@ -1,0 +1,86 @@
+"""World-size-2 test of the multi-GPU control flow on CPU (gloo): slab-local scatter -> ONE all-reduce of the
+screen-space gradient rows -> replicated parameter gradients.  The CUDA stages are replaced by the oracle's
+(oracle.render_backward / oracle.preprocess_backward), the control flow under test is
+rade_gs_b200.multigpu.backward_two_stage / allreduce_sum_ / partition_tile_rows -- the same code the GPU path runs
+with NCCL."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN_CASES, ROOT, golden_oracle_inputs, golden_upstream, load_golden
+
+SG_KEYS = ("mean2D", "conic", "opacity", "colors", "ts", "camera_planes", "ray_planes", "normals", "view_points")
+
+
+def _slab_upstream(up, H, rows):
+    """Upstream gradients restricted to a slab of pixel rows: every per-pixel term of backward-render is linear in
+    that pixel's upstream gradients, so zeroing the other rows yields exactly the slab's partial sums."""
+    out = {}
+    for k, v in up.items():
+        z = np.zeros_like(v)
+        z[:, rows[0]:rows[1], :] = v[:, rows[0]:rows[1], :]
+        out[k] = z
+    return out
+
+
+def _worker(rank, world, port, case, tmpdir):
+    for p in (os.path.join(ROOT, "rade-gs_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import oracle
+    from rade_gs_b200 import multigpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d = load_golden(case)
+        inp = golden_oracle_inputs(d)
+        H = inp.H
+        fwd = oracle.forward(inp)  # replicated on every rank, like preprocess on the GPUs
+        slabs = multigpu.partition_tile_rows(multigpu.tile_rows(H), world)
+        rows = (min(slabs[rank][0] * 16, H), min(slabs[rank][1] * 16, H))
+        up = _slab_upstream(golden_upstream(d), H, rows)
+
+        def stage1():
+            sg = oracle.render_backward(inp, fwd, up)
+            return torch.from_numpy(np.concatenate([sg[k].reshape(inp.P, -1) for k in SG_KEYS], axis=1))
+
+        def stage2(acc):
+            a = acc.numpy()
+            sg, o = {}, 0
+            for k, w in zip(SG_KEYS, (3, 4, 1, 3, 1, 6, 2, 3, 3)):
+                sg[k] = np.ascontiguousarray(a[:, o:o + w]).reshape(-1) if w == 1 else np.ascontiguousarray(a[:, o:o + w])
+                o += w
+            return oracle.preprocess_backward(inp, fwd, sg)
+
+        out = multigpu.backward_two_stage(stage1, stage2)
+        np.savez(os.path.join(tmpdir, f"rank{rank}.npz"), **{k: v for k, v in out.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [c for c in ("depth_ks01", "coord_ks0") if c in GOLDEN_CASES])
+def test_two_rank_backward_equals_single(case, tmp_path):
+    import oracle
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
+    d = load_golden(case)
+    inp = golden_oracle_inputs(d)
+    fwd = oracle.forward(inp)
+    single = oracle.backward(inp, fwd, golden_upstream(d))
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rotations"):
+        assert np.array_equal(r0[k], r1[k]), k  # replicated result
+        ref = single[k]
+        err = np.abs(r0[k] - ref).max()
+        assert err <= 1e-5 * max(1.0, np.abs(ref).max()), (k, err)  # float64 partial sums: association only
+
+
+def test_allreduce_is_noop_without_process_group():
+    from rade_gs_b200.multigpu import allreduce_sum_
+    t = torch.arange(6.0)
+    assert torch.equal(allreduce_sum_(t.clone()), t)

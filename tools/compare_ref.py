@@ -51,7 +51,7 @@ def main():
 
     dev = torch.device("cuda:0")
     if a.cfg == "small":
-        sc = scenes.make_scene(20000, 320, 240, 300.0, -3.6)
+        sc = scenes.make_scene(20000, 320, 240, 300.0, -3.6, view=scenes.look_at_view((0.4, -0.3, -0.5), (0.1, 0.05, 6.0)), bg=(0.1, 0.2, 0.3))
         coord, depth = False, True
     else:
         sc, coord, depth = scenes.make_config(a.cfg)
