@@ -31,6 +31,48 @@ __device__ __forceinline__ float hypot_nr(float a, float b) {  // sqrt(a^2+b^2) 
 	return absb * sqrtf(1.f + absa);
 }
 
+// One implicit-shift QL sweep on the unreduced block [L..M] of the tridiagonal (d, e), rotations accumulated in z
+// (auxiliary.h:355-388).  L and M are compile-time so every array index is static.
+template <int L, int M>
+__device__ __forceinline__ void ql_sweep(float (&d)[3], float (&e)[3], float (&z)[3][3]) {
+	float g = (d[L + 1] - d[L]) / (2 * e[L]);
+	float r = hypot_nr(g, 1.f);
+	g = d[M] - d[L] + e[L] / (g + ((g >= 0.f) ? fabsf(r) : -fabsf(r)));
+	float s = 1.f, c = 1.f, p = 0.f;
+	bool underflow = false;  // the reference's early `break` (r ~ 0)
+#pragma unroll
+	for (int i = M - 1; i >= L; i--) {
+		if (!underflow) {
+			float f = s * e[i];
+			const float b = c * e[i];
+			e[i + 1] = r = hypot_nr(f, g);
+			if (fabsf(r) <= kEigEps) {
+				d[i + 1] -= p;
+				e[M] = 0.f;
+				underflow = true;
+			} else {
+				s = f / r;
+				c = g / r;
+				g = d[i + 1] - p;
+				r = (d[i] - g) * s + 2 * c * b;
+				d[i + 1] = g + (p = s * r);
+				g = c * r - b;
+#pragma unroll
+				for (int k = 0; k < 3; k++) {
+					f = z[k][i + 1];
+					z[k][i + 1] = s * z[k][i] + c * f;
+					z[k][i] = c * z[k][i] - s * f;
+				}
+			}
+		}
+	}
+	if (!underflow) {
+		d[L] -= p;
+		e[L] = g;
+		e[M] = 0.f;
+	}
+}
+
 // Eigen-decomposition of the symmetric matrix with packed upper triangle cov = (xx,xy,xz,yy,yz,zz).
 // lam[k] / column k of `vec` are an eigenpair.  Returns false if a QL sweep did not converge in 30 iterations
 // (the reference then zeroes the geometry terms, forward.cu:162-168).
@@ -109,52 +151,27 @@ __device__ inline bool eig_sym3_tql(const float cov[6], float lam[3], M3& vec) {
 	z[1][2] = z[2][1] = 0.f;
 
 	// ---- implicit QL on the tridiagonal (d, e) ----
+	// The reference loops l = 0..2 with run-time m and i; here l is unrolled and m dispatched through templates so
+	// that d, e, z are indexed statically and stay in registers (same operations in the same order).
 	e[0] = e[1];
 	e[1] = e[2];
 	e[2] = 0.f;
-#pragma unroll 1
-	for (int l = 0; l < 3; l++) {
+	{  // l = 0
 		int iter = 0;
-		int m;
-		do {
-			for (m = l; m < 2; m++) {
-				if (fabsf(fabsf(e[m])) <= kEigEps) break;
-			}
-			if (m != l) {
-				if (iter++ == 30) return false;
-				float g = (d[l + 1] - d[l]) / (2 * e[l]);
-				float r = hypot_nr(g, 1.f);
-				g = d[m] - d[l] + e[l] / (g + ((g >= 0.f) ? fabsf(r) : -fabsf(r)));
-				float s = 1.f, c = 1.f, p = 0.f;
-				int i;
-				for (i = m - 1; i >= l; i--) {
-					float f = s * e[i];
-					const float b = c * e[i];
-					e[i + 1] = r = hypot_nr(f, g);
-					if (fabsf(r) <= kEigEps) {
-						d[i + 1] -= p;
-						e[m] = 0.f;
-						break;
-					}
-					s = f / r;
-					c = g / r;
-					g = d[i + 1] - p;
-					r = (d[i] - g) * s + 2 * c * b;
-					d[i + 1] = g + (p = s * r);
-					g = c * r - b;
-#pragma unroll
-					for (int k = 0; k < 3; k++) {
-						f = z[k][i + 1];
-						z[k][i + 1] = s * z[k][i] + c * f;
-						z[k][i] = c * z[k][i] - s * f;
-					}
-				}
-				if (fabsf(r) <= kEigEps && i >= l) continue;
-				d[l] -= p;
-				e[l] = g;
-				e[m] = 0.f;
-			}
-		} while (m != l);
+		while (true) {
+			const int m = (fabsf(fabsf(e[0])) <= kEigEps) ? 0 : ((fabsf(fabsf(e[1])) <= kEigEps) ? 1 : 2);
+			if (m == 0) break;
+			if (iter++ == 30) return false;
+			if (m == 1) ql_sweep<0, 1>(d, e, z); else ql_sweep<0, 2>(d, e, z);
+		}
+	}
+	{  // l = 1
+		int iter = 0;
+		while (true) {
+			if (fabsf(fabsf(e[1])) <= kEigEps) break;
+			if (iter++ == 30) return false;
+			ql_sweep<1, 2>(d, e, z);
+		}
 	}
 	lam[0] = d[0];
 	lam[1] = d[1];
@@ -169,6 +186,7 @@ struct SigmaInv {
 	M3 inv;          // Vrk_inv
 	M3 E;            // eigenvectors (columns)
 	float lam[3];
+	float lam_min;
 	int min_id;
 	bool well;
 	bool solved;     // eigen-solver converged
@@ -179,12 +197,13 @@ __device__ __forceinline__ SigmaInv sigma_inverse(const float cov3D[6]) {
 	s.solved = eig_sym3_tql(cov3D, s.lam, s.E);
 	const float* l = s.lam;
 	s.min_id = l[0] > l[1] ? (l[1] > l[2] ? 2 : 1) : (l[0] > l[2] ? 2 : 0);
-	s.well = l[s.min_id] > 0.00000001f;
+	s.lam_min = s.min_id == 0 ? l[0] : (s.min_id == 1 ? l[1] : l[2]);
+	s.well = s.lam_min > 0.00000001f;
 	if (s.well) {
 		const M3 diag = m3(1 / l[0], 0.f, 0.f, 0.f, 1 / l[1], 0.f, 0.f, 0.f, 1 / l[2]);
 		s.inv = s.E * diag * transpose(s.E);
 	} else {
-		const V3 em = s.E.c[s.min_id];
+		const V3 em = s.min_id == 0 ? s.E.c[0] : (s.min_id == 1 ? s.E.c[1] : s.E.c[2]);
 		s.inv = outer(em, em);
 	}
 	return s;

@@ -176,12 +176,12 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, G
 					const M3 dViT = transpose(dVi);
 					M3 sym;
 					sym.c[0] = dVi.c[0] + dViT.c[0]; sym.c[1] = dVi.c[1] + dViT.c[1]; sym.c[2] = dVi.c[2] + dViT.c[2];
-					const V3 emin = si.E.c[si.min_id];
+					const V3 emin = si.min_id == 0 ? si.E.c[0] : (si.min_id == 1 ? si.E.c[1] : si.E.c[2]);
 					const V3 dLdv = mulcol(sym, emin);
 #pragma unroll
 					for (int j = 0; j < 3; j++) {
 						if (j != si.min_id) {
-							const float scale = dot3(si.E.c[j], dLdv) / min(si.lam[si.min_id] - si.lam[j], -0.0000001f);
+							const float scale = dot3(si.E.c[j], dLdv) / min(si.lam_min - si.lam[j], -0.0000001f);
 							const M3 o = outer(si.E.c[j] * scale, emin);
 							dL_dVrk.c[0] = dL_dVrk.c[0] + o.c[0]; dL_dVrk.c[1] = dL_dVrk.c[1] + o.c[1]; dL_dVrk.c[2] = dL_dVrk.c[2] + o.c[2];
 						}
@@ -347,19 +347,22 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, G
 			}
 			const int ncoef = (deg + 1) * (deg + 1);
 			float3 dL_ddir = {0.f, 0.f, 0.f};
-			for (int k = 0; k < M; k++) {
-				float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-				if (k < ncoef) {
-					o0 = basis[k] * dRGB[0]; o1 = basis[k] * dRGB[1]; o2 = basis[k] * dRGB[2];
-					if (k > 0) {
-						const float s0 = __ldg(sh + 3 * k), s1 = __ldg(sh + 3 * k + 1), s2 = __ldg(sh + 3 * k + 2);
-						const float sd = s0 * dRGB[0] + s1 * dRGB[1] + s2 * dRGB[2];
-						dL_ddir.x += ddx[k] * sd;
-						dL_ddir.y += ddy[k] * sd;
-						dL_ddir.z += ddz[k] * sd;
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				if (k < M) {
+					float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+					if (k < ncoef) {
+						o0 = basis[k] * dRGB[0]; o1 = basis[k] * dRGB[1]; o2 = basis[k] * dRGB[2];
+						if (k > 0) {
+							const float s0 = __ldg(sh + 3 * k), s1 = __ldg(sh + 3 * k + 1), s2 = __ldg(sh + 3 * k + 2);
+							const float sd = s0 * dRGB[0] + s1 * dRGB[1] + s2 * dRGB[2];
+							dL_ddir.x += ddx[k] * sd;
+							dL_ddir.y += ddy[k] * sd;
+							dL_ddir.z += ddz[k] * sd;
+						}
 					}
+					dsh[3 * k] = o0; dsh[3 * k + 1] = o1; dsh[3 * k + 2] = o2;
 				}
-				dsh[3 * k] = o0; dsh[3 * k + 1] = o1; dsh[3 * k + 2] = o2;
 			}
 			// through the normalisation of the view direction (auxiliary.h:123-133)
 			const float sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;

@@ -41,9 +41,18 @@ def test_preprocess_state(golden):
     # exact: what feeds the keys
     assert np.array_equal(g["depths"][vis].view(np.int32), d["st_depths"][vis].view(np.int32))
     assert np.array_equal(g["means2D"][vis].view(np.int32), d["st_means2D"][vis].view(np.int32))
-    assert np.array_equal(g["clamped"][vis].astype(bool), d["st_clamped"][vis].astype(bool))
+    # the reference leaves rgb/clamped (cov3D) unwritten when colours (covariances) are precomputed
+    skip = set()
+    if "in_colors_precomp" in d:
+        skip |= {"rgb", "clamped"}
+    if "in_cov3D_precomp" in d:
+        skip |= {"cov3D"}
+    if "clamped" not in skip:
+        assert np.array_equal(g["clamped"][vis].astype(bool), d["st_clamped"][vis].astype(bool))
     # float state: all but a few degenerate splats within 1e-4 relative
     for k, tol in (("conic_opacity", 1e-3), ("rgb", 1e-5), ("ts", 1e-5), ("cov3D", 1e-5), ("view_points", 1e-5)):
+        if k in skip:
+            continue
         a, r = g[k][vis].reshape(vis.sum(), -1), d["st_" + k][vis].reshape(vis.sum(), -1)
         bad = (np.abs(a - r) > tol * (1 + np.abs(r))).any(axis=1)
         assert bad.mean() <= 0.01, (k, bad.mean())
