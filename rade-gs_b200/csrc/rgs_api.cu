@@ -5,6 +5,7 @@
 // 254-425, 429-571, 176-188; cuda_rasterizer/rasterizer_impl.h:22-94).
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -100,6 +101,8 @@ static ImgView carve_img(char* base, int tiles, size_t N, bool coord, bool depth
 	Carver c(base);
 	ImgView v;
 	v.ranges = c.take<uint2>(tiles);
+	v.tile_count = c.take<uint32_t>(tiles);
+	v.totals = c.take<uint32_t>(2);
 	v.n_contrib = c.take<uint32_t>(2 * N);
 	v.accum_depth = c.take<float>(depth ? N : 0);
 	v.normal_length = c.take<float>((coord || depth) ? N : 0);
@@ -212,26 +215,41 @@ int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_fo
 	GeomView g = carve_geom(geom_ptr, P, p.coord, scan_bytes, nullptr);
 
 	int64_t R = 0;
+	uint32_t max_list = 0;
 	if (P > 0) {
-		{ StageScope sc(ST_PREPROCESS, s); launch_preprocess_forward(p, g, out->radii, s); }
+		RGS_CUDA_TRY(cudaMemsetAsync(img.tile_count, 0, (size_t)tiles * sizeof(uint32_t), s));
+		{ StageScope sc(ST_PREPROCESS, s); launch_preprocess_forward(p, g, out->radii, img.tile_count, s); }
 		if ((rc = debug_sync(cam, s, "preprocess")) != RGS_OK) return rc;
-		{ StageScope sc(ST_SCAN, s); launch_scan(g, P, s); }
-		// the one host sync of the forward pass: instance count sizes the binning buffers and is returned to the
-		// caller (reference: blocking cudaMemcpy, rasterizer_impl.cu:354)
+		{ StageScope sc(ST_SCAN, s); launch_tile_scan(p, img, s); }
+		// the one host sync of the forward pass: the instance count sizes the binning buffers and is returned to the
+		// caller (reference: blocking cudaMemcpy, rasterizer_impl.cu:354); the longest tile list picks the sort path
 		uint32_t* box = pinned_mailbox();
 		if (!box) return fail(RGS_E_CUDA, "cudaHostAlloc failed for the num_rendered mailbox");
-		RGS_CUDA_TRY(cudaMemcpyAsync(box, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		RGS_CUDA_TRY(cudaMemcpyAsync(box, img.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 		RGS_CUDA_TRY(cudaStreamSynchronize(s));
-		R = (int64_t)*box;
+		R = (int64_t)box[0];
+		max_list = box[1];
 	}
-	const size_t sort_bytes = R > 0 ? sort_temp_bytes((size_t)R) : 0;
+	static const bool force_radix = getenv("RGS_BINNING") != nullptr && std::string(getenv("RGS_BINNING")) == "radix";
+	const bool tile_path = !force_radix && max_list <= (uint32_t)TILE_SORT_CAP;
+	const size_t sort_bytes = (R > 0 && !tile_path) ? sort_temp_bytes((size_t)R) : 0;
 	size_t bin_bytes = 0;
 	carve_bin(nullptr, (size_t)R, sort_bytes, &bin_bytes);
 	char* bin_ptr = bufs->binning(bufs->binning_user, bin_bytes);
 	if (!bin_ptr) return fail(RGS_E_ALLOC, "binning buffer callback returned NULL");
 	BinView b = carve_bin(bin_ptr, (size_t)R, sort_bytes, nullptr);
 
-	{ StageScope sc(ST_BINNING, s); launch_binning(p, g, b, img, out->radii, R, s); }
+	if (P == 0) {
+		RGS_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, (size_t)tiles * sizeof(uint2), s));
+	} else if (tile_path) {
+		StageScope sc(ST_BINNING, s);
+		launch_tile_binning(p, g, b, img, out->radii, R, max_list, s);
+	} else {
+		// a tile list too long for the shared-memory sort: global radix path (Gaussian-major offsets + 45-bit sort)
+		StageScope sc(ST_BINNING, s);
+		launch_scan(g, P, s);
+		launch_binning(p, g, b, img, out->radii, R, s);
+	}
 	if ((rc = debug_sync(cam, s, "binning")) != RGS_OK) return rc;
 	{ StageScope sc(ST_RENDER_FWD, s); launch_render_forward(p, g, b, img, ro, s); }
 	if ((rc = debug_sync(cam, s, "render")) != RGS_OK) return rc;

@@ -102,4 +102,241 @@ void launch_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, cons
 	count_launch(2 + 8);
 }
 
+
+// =====================================================================================================================
+// Tile-bucket binning (default path).
+//
+// The reference sorts all R instances globally on 45-bit (tile | depth) keys: six 8-bit onesweep passes, each
+// reading and writing 12 B per instance.  The same total order is (tile, depth bits, Gaussian index), so it can be
+// produced with one bucketing step and one local sort instead:
+//   1. preprocess counts instances per tile (one red.global.add per (splat, tile));
+//   2. tile_scan_kernel: exclusive scan of the T counters -> ranges[tile] = [start, end), num_rendered, longest list;
+//   3. scatter_kernel: every instance takes a slot inside its tile's segment (counter counted back down) and
+//      stores the 64-bit local key (depth bits << 32 | Gaussian index) -- 8 B written once;
+//   4. tile_sort_kernel: one CTA per tile loads its segment into shared memory, merge-sorts the 64-bit keys
+//      (register network for runs of 8, then merge-path passes) and writes the ids (and the reference-format keys).
+// Equal depth bits fall back to the Gaussian index through the low key half, which is exactly what the reference's
+// stable sort yields (instances are emitted in ascending Gaussian index).  Global traffic: 8 B + 8 B + 4 B (+ 8 B
+// for the exported keys) per instance instead of ~156 B.
+// Lists longer than TILE_SORT_CAP (shared-memory capacity) make the host take the radix path above instead.
+// =====================================================================================================================
+
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+                                                          uint32_t* __restrict__ totals) {
+	__shared__ uint32_t s_warp[32];
+	__shared__ uint32_t s_carry, s_max;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) { s_carry = 0; s_max = 0; }
+	__syncthreads();
+	uint32_t local_max = 0;
+	for (int base = 0; base < tiles; base += 1024) {
+		const int t = base + tid;
+		const uint32_t c = t < tiles ? tile_count[t] : 0u;
+		local_max = max(local_max, c);
+		uint32_t v = c;  // inclusive warp scan
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+			if (lane >= o) v += n;
+		}
+		if (lane == 31) s_warp[warp] = v;
+		__syncthreads();
+		if (warp == 0) {
+			uint32_t w = s_warp[lane];
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
+				if (lane >= o) w += n;
+			}
+			s_warp[lane] = w;
+		}
+		__syncthreads();
+		const uint32_t carry = s_carry;
+		const uint32_t incl = carry + v + (warp > 0 ? s_warp[warp - 1] : 0u);
+		if (t < tiles) ranges[t] = c ? make_uint2(incl - c, incl) : make_uint2(0u, 0u);  // empty tiles stay (0,0) like the reference's memset
+		__syncthreads();
+		if (tid == 1023) s_carry = incl;
+		__syncthreads();
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+	if (lane == 0) atomicMax(&s_max, local_max);
+	__syncthreads();
+	if (tid == 0) { totals[0] = s_carry; totals[1] = s_max; }
+}
+
+void launch_tile_scan(const FwdParams& p, ImgView img, cudaStream_t s) {
+	tile_scan_kernel<<<1, 1024, 0, s>>>(p.grid_x * p.grid_y, img.tile_count, img.ranges, img.totals);
+	count_launch();
+}
+
+// Scatter: every instance takes a slot inside its tile's segment and stores its 64-bit local key.
+// A warp owns 32 consecutive Gaussians and emits them COOPERATIVELY: the tiles of one splat are spread over the lanes
+// (lane k takes the k-th tile of the rectangle), four splats are in flight per round so that the returning atomics
+// (slot = counter counted back down) of one splat overlap the key stores of the previous ones.  A thread-per-splat
+// loop would serialise one ~1 us atomic round trip per tile and let a few large splats hold the whole grid.
+__global__ void __launch_bounds__(256) scatter_kernel(int P, const float* __restrict__ records, int rec_f, const float* __restrict__ depths,
+                                                       const uint32_t* __restrict__ tiles_touched, const int* __restrict__ radii, int grid_x, int grid_y,
+                                                       int row_begin, int row_end, const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_count,
+                                                       uint64_t* __restrict__ local_keys) {
+	const int lane = threadIdx.x & 31;
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	int cnt = 0, x0 = 0, y0 = 0, w = 1;
+	uint32_t dbits = 0;
+	if (idx < P) {
+		cnt = (int)tiles_touched[idx];
+		if (cnt > 0) {
+			const float2 xy = *reinterpret_cast<const float2*>(records + (size_t)idx * rec_f);
+			uint2 rmin, rmax;
+			tile_rect(xy, radii[idx], grid_x, grid_y, rmin, rmax);
+			x0 = (int)rmin.x;
+			w = (int)rmax.x - (int)rmin.x;
+			y0 = max((int)rmin.y, row_begin);
+			dbits = __float_as_uint(depths[idx]);
+		}
+	}
+	unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
+	while (live) {
+		int s_cnt[4], s_x0[4], s_y0[4], s_w[4], s_tile[4];
+		uint32_t s_slot[4];
+		uint64_t s_key[4];
+		bool act[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			act[u] = false;
+			s_cnt[u] = 0;
+			if (live) {
+				const int src = __ffs(live) - 1;
+				live &= live - 1;
+				s_cnt[u] = __shfl_sync(0xffffffffu, cnt, src);
+				s_x0[u] = __shfl_sync(0xffffffffu, x0, src);
+				s_y0[u] = __shfl_sync(0xffffffffu, y0, src);
+				s_w[u] = __shfl_sync(0xffffffffu, w, src);
+				const uint32_t db = __shfl_sync(0xffffffffu, dbits, src);
+				s_key[u] = ((uint64_t)db << 32) | (uint32_t)(idx - lane + src);
+				if (lane < s_cnt[u]) {
+					const int ry = lane / s_w[u], rx = lane - ry * s_w[u];
+					s_tile[u] = (s_y0[u] + ry) * grid_x + s_x0[u] + rx;
+					s_slot[u] = atomicSub(tile_count + s_tile[u], 1u) - 1u;
+					act[u] = true;
+				}
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < 4; u++)
+			if (act[u]) local_keys[ranges[s_tile[u]].x + s_slot[u]] = s_key[u];
+		// splats covering more than 32 tiles: remaining tiles, 32 per round
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			for (int k = lane + 32; k < s_cnt[u]; k += 32) {
+				const int ry = k / s_w[u], rx = k - ry * s_w[u];
+				const int t = (s_y0[u] + ry) * grid_x + s_x0[u] + rx;
+				const uint32_t slot = atomicSub(tile_count + t, 1u) - 1u;
+				local_keys[ranges[t].x + slot] = s_key[u];
+			}
+		}
+	}
+}
+
+// ---- per-tile sort: shared-memory merge sort of the 64-bit local keys ------------------------------------------------
+// One CTA per tile.  Each thread sorts 8 consecutive keys in registers (odd-even merge network, 19 compare-exchanges),
+// then log2(n/8) merge passes ping-pong between two shared buffers; in a pass every thread produces 8 consecutive
+// outputs: it locates its start in the two input runs with a merge-path binary search and merges sequentially.
+// ~100 instructions per key in total (a shared-memory bitonic network needs ~500).
+constexpr int SORT_VT = 8;
+constexpr uint64_t KEY_MAX = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ void cswap(uint64_t& a, uint64_t& b) {
+	const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
+	a = lo;
+	b = hi;
+}
+
+// Shared-memory index with one pad slot per 16 keys: a thread's merge window starts ~4 keys after its neighbour's,
+// i.e. 32 B apart -- unpadded that is an 8-way bank conflict on every step of the merge.
+__device__ __forceinline__ int spad(int e) { return e + (e >> 4); }
+constexpr int SORT_THREADS = 128;
+
+__global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, int grid_x, int row_begin,
+                                                                  const uint64_t* __restrict__ local_keys, uint32_t* __restrict__ point_list,
+                                                                  uint64_t* __restrict__ keys_sorted, int cap) {
+	extern __shared__ uint64_t s_keys[];  // [2][spad(cap)]
+	const int tile = (blockIdx.y + row_begin) * grid_x + blockIdx.x;
+	const uint2 rg = ranges[tile];
+	const int n = (int)(rg.y - rg.x);
+	if (n == 0) return;
+	const int tid = threadIdx.x;
+	uint64_t* bufA = s_keys;
+	uint64_t* bufB = s_keys + spad(cap);
+	const uint64_t* src = local_keys + rg.x;
+	// runs of 8 straight from global memory: register sorting network (Batcher odd-even merge sort for 8 inputs)
+	for (int o0 = tid * SORT_VT; o0 < n; o0 += SORT_THREADS * SORT_VT) {
+		uint64_t k[SORT_VT];
+#pragma unroll
+		for (int q = 0; q < SORT_VT; q++) k[q] = (o0 + q < n) ? src[o0 + q] : KEY_MAX;
+		cswap(k[0], k[1]); cswap(k[2], k[3]); cswap(k[4], k[5]); cswap(k[6], k[7]);
+		cswap(k[0], k[2]); cswap(k[1], k[3]); cswap(k[4], k[6]); cswap(k[5], k[7]);
+		cswap(k[1], k[2]); cswap(k[5], k[6]);
+		cswap(k[0], k[4]); cswap(k[1], k[5]); cswap(k[2], k[6]); cswap(k[3], k[7]);
+		cswap(k[2], k[4]); cswap(k[3], k[5]);
+		cswap(k[1], k[2]); cswap(k[3], k[4]); cswap(k[5], k[6]);
+#pragma unroll
+		for (int q = 0; q < SORT_VT; q++)
+			if (o0 + q < n) bufA[spad(o0 + q)] = k[q];
+	}
+	__syncthreads();
+	uint64_t* in = bufA;
+	uint64_t* out = bufB;
+	for (int L = SORT_VT; L < n; L <<= 1) {
+		for (int o0 = tid * SORT_VT; o0 < n; o0 += SORT_THREADS * SORT_VT) {
+			const int base = (o0 / (2 * L)) * (2 * L);
+			const int a0 = base, lenA = min(L, n - base);
+			const int b0 = base + lenA, lenB = max(0, min(L, n - b0));
+			const int diag = o0 - base;
+			int lo = max(0, diag - lenB), hi = min(diag, lenA);
+			while (lo < hi) {  // merge path: smallest i with A[i] > B[diag-1-i]
+				const int mid = (lo + hi) >> 1;
+				if (in[spad(a0 + mid)] <= in[spad(b0 + diag - 1 - mid)]) lo = mid + 1; else hi = mid;
+			}
+			int i = lo, j = diag - lo;
+			uint64_t ka = i < lenA ? in[spad(a0 + i)] : KEY_MAX, kb = j < lenB ? in[spad(b0 + j)] : KEY_MAX;
+#pragma unroll
+			for (int q = 0; q < SORT_VT; q++) {
+				if (o0 + q < n) {
+					const bool take_a = ka <= kb;  // exhausted runs read as KEY_MAX; keys are unique, KEY_MAX never occurs
+					out[spad(o0 + q)] = take_a ? ka : kb;
+					if (take_a) { i++; ka = i < lenA ? in[spad(a0 + i)] : KEY_MAX; } else { j++; kb = j < lenB ? in[spad(b0 + j)] : KEY_MAX; }
+				}
+			}
+		}
+		__syncthreads();
+		uint64_t* t = in; in = out; out = t;
+	}
+	uint32_t* dst = point_list + rg.x;
+	uint64_t* kdst = keys_sorted + rg.x;
+	const uint64_t tile_hi = (uint64_t)tile << 32;
+	for (int i = tid; i < n; i += SORT_THREADS) {
+		const uint64_t k = in[spad(i)];
+		dst[i] = (uint32_t)k;
+		kdst[i] = tile_hi | (k >> 32);
+	}
+}
+
+void launch_tile_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, const int* radii, int64_t R, uint32_t max_list, cudaStream_t s) {
+	if (R <= 0 || p.row_end <= p.row_begin) return;
+	scatter_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p.P, g.records, rec_floats(p.coord), g.depths, g.tiles_touched, radii, p.grid_x, p.grid_y,
+	                                                  p.row_begin, p.row_end, img.ranges, img.tile_count, b.keys_unsorted);
+	const int cap = (max((int)max_list, 256) + 255) & ~255;  // keys per ping-pong buffer
+	const size_t smem = (size_t)2 * (cap + (cap >> 4)) * sizeof(uint64_t);
+	static size_t configured = 0;
+	if (smem > 48 * 1024 && smem > configured) {
+		const size_t most = (size_t)2 * (TILE_SORT_CAP + (TILE_SORT_CAP >> 4)) * sizeof(uint64_t);
+		cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
+		configured = most;
+	}
+	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
+	tile_sort_kernel<<<grid, SORT_THREADS, smem, s>>>(img.ranges, p.grid_x, p.row_begin, b.keys_unsorted, b.point_list, b.keys_sorted, cap);
+	count_launch(2);
+}
+
 }  // namespace rgs

@@ -73,6 +73,8 @@ struct BinView {
 
 struct ImgView {
 	uint2* ranges;        // [tiles]
+	uint32_t* tile_count; // [tiles] instances per tile (tile-bucket binning); counted down to 0 by the scatter
+	uint32_t* totals;     // [2]     num_rendered, longest tile list
 	uint32_t* n_contrib;  // [2 * N]
 	float* accum_depth;   // [N]
 	float* normal_length; // [N]
@@ -185,7 +187,7 @@ struct FwdParams {
 	const float *viewmatrix, *projmatrix, *cam_pos, *background;
 };
 
-void launch_preprocess_forward(const FwdParams& p, GeomView g, int* radii, cudaStream_t s);
+void launch_preprocess_forward(const FwdParams& p, GeomView g, int* radii, uint32_t* tile_count, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
 
 size_t scan_temp_bytes(int P);
@@ -193,6 +195,10 @@ size_t sort_temp_bytes(size_t R);
 // inclusive scan of tiles_touched -> offsets; writes the total to *total_dev (pinned or device memory)
 void launch_scan(GeomView g, int P, cudaStream_t s);
 void launch_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, const int* radii, int64_t R, cudaStream_t s);
+// tile-bucket binning (default path): per-tile counts -> ranges/totals -> scatter -> per-tile shared-memory sort
+constexpr int TILE_SORT_CAP = 8192;   // longest tile list the shared-memory sort takes (2 x 64 KB ping-pong); longer lists use the radix path
+void launch_tile_scan(const FwdParams& p, ImgView img, cudaStream_t s);
+void launch_tile_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, const int* radii, int64_t R, uint32_t max_list, cudaStream_t s);
 
 struct RenderOut {
 	float *color, *coord, *mcoord, *alpha, *normal, *depth, *mdepth;

@@ -65,7 +65,7 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
 	return float3{fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f)};
 }
 
-__global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, GeomView g, int* __restrict__ radii) {
+__global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, GeomView g, int* __restrict__ radii, uint32_t* __restrict__ tile_count) {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= p.P) return;
 
@@ -206,6 +206,11 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
 				const int ry0 = max((int)rect_min.y, p.row_begin);
 				const int ry1 = min((int)rect_max.y, p.row_end);
 				my_tiles = (rect_max.x - rect_min.x) * (uint32_t)max(0, ry1 - ry0);
+				// tile-bucket binning: one counter per tile (red.global.add, no return value needed)
+				if (tile_count != nullptr) {
+					for (int y = ry0; y < ry1; y++)
+						for (int x = rect_min.x; x < (int)rect_max.x; x++) atomicAdd(tile_count + (y * p.grid_x + x), 1u);
+				}
 			}
 		}
 	}
@@ -213,10 +218,10 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
 	g.tiles_touched[idx] = my_tiles;
 }
 
-void launch_preprocess_forward(const FwdParams& p, GeomView g, int* radii, cudaStream_t s) {
+void launch_preprocess_forward(const FwdParams& p, GeomView g, int* radii, uint32_t* tile_count, cudaStream_t s) {
 	const int threads = 256;
 	const int blocks = (p.P + threads - 1) / threads;
-	preprocess_forward_kernel<<<blocks, threads, 0, s>>>(p, g, radii);
+	preprocess_forward_kernel<<<blocks, threads, 0, s>>>(p, g, radii, tile_count);
 	count_launch();
 }
 

@@ -17,22 +17,16 @@
 
 namespace rgs {
 
-__global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, GeomView g, const int* __restrict__ radii,
+__global__ void __launch_bounds__(128, 4) preprocess_backward_kernel(FwdParams p, GeomView g, const int* __restrict__ radii,
                                                                    const float* __restrict__ grad_accum, ParamGradOut out, int fix_mip) {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= p.P) return;
-	const int M = p.M;
 	const bool visible = radii[idx] > 0;
 
 	float o_means2D[3] = {0, 0, 0}, o_colors[3] = {0, 0, 0}, o_opacity = 0.f, o_mean3D[3] = {0, 0, 0};
 	float o_cov[6] = {0, 0, 0, 0, 0, 0}, o_scale[3] = {0, 0, 0}, o_rot[4] = {0, 0, 0, 0};
 
-	if (!visible) {
-		if (out.d_sh != nullptr) {
-			float* dsh = out.d_sh + (size_t)idx * M * 3;
-			for (int i = 0; i < 3 * M; i++) dsh[i] = 0.f;
-		}
-	} else {
+	if (visible) {
 		const int GF = grad_floats(p.coord);
 		const float* ga = grad_accum + (size_t)idx * GF;
 		float gr[GRAD_FLOATS_COORD];
@@ -305,72 +299,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, G
 			dL_dmean.z += d1.z + d2.z;
 		}
 
-		// ---- SH backward (backward.cu:21-140) ----
-		if (p.shs != nullptr) {
-			const float3 campos = {p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]};
-			const float3 dir_orig = {mean.x - campos.x, mean.y - campos.y, mean.z - campos.z};
-			const float dlen = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-			const float x = dir_orig.x / dlen, y = dir_orig.y / dlen, z = dir_orig.z / dlen;
-			const uint8_t cb = g.clamped[idx];
-			const float dRGB[3] = {(cb & 1) ? 0.f : o_colors[0], (cb & 2) ? 0.f : o_colors[1], (cb & 4) ? 0.f : o_colors[2]};
-			const float* sh = p.shs + (size_t)idx * M * 3;
-			float* dsh = out.d_sh + (size_t)idx * M * 3;
-			const int deg = p.D;
-			float basis[16];
-			float ddx[16], ddy[16], ddz[16];  // d(basis_k)/d(dir)
-#pragma unroll
-			for (int k = 0; k < 16; k++) { basis[k] = 0.f; ddx[k] = 0.f; ddy[k] = 0.f; ddz[k] = 0.f; }
-			basis[0] = kSH0;
-			if (deg > 0) {
-				basis[1] = -kSH1 * y; basis[2] = kSH1 * z; basis[3] = -kSH1 * x;
-				ddx[3] = -kSH1; ddy[1] = -kSH1; ddz[2] = kSH1;
-				if (deg > 1) {
-					const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-					basis[4] = kSH2[0] * xy; basis[5] = kSH2[1] * yz; basis[6] = kSH2[2] * (2.f * zz - xx - yy);
-					basis[7] = kSH2[3] * xz; basis[8] = kSH2[4] * (xx - yy);
-					ddx[4] = kSH2[0] * y; ddx[6] = kSH2[2] * 2.f * -x; ddx[7] = kSH2[3] * z; ddx[8] = kSH2[4] * 2.f * x;
-					ddy[4] = kSH2[0] * x; ddy[5] = kSH2[1] * z; ddy[6] = kSH2[2] * 2.f * -y; ddy[8] = kSH2[4] * 2.f * -y;
-					ddz[5] = kSH2[1] * y; ddz[6] = kSH2[2] * 2.f * 2.f * z; ddz[7] = kSH2[3] * x;
-					if (deg > 2) {
-						basis[9] = kSH3[0] * y * (3.f * xx - yy); basis[10] = kSH3[1] * xy * z;
-						basis[11] = kSH3[2] * y * (4.f * zz - xx - yy); basis[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-						basis[13] = kSH3[4] * x * (4.f * zz - xx - yy); basis[14] = kSH3[5] * z * (xx - yy);
-						basis[15] = kSH3[6] * x * (xx - 3.f * yy);
-						ddx[9] = kSH3[0] * 3.f * 2.f * xy; ddx[10] = kSH3[1] * yz; ddx[11] = kSH3[2] * -2.f * xy; ddx[12] = kSH3[3] * -3.f * 2.f * xz;
-						ddx[13] = kSH3[4] * (-3.f * xx + 4.f * zz - yy); ddx[14] = kSH3[5] * 2.f * xz; ddx[15] = kSH3[6] * 3.f * (xx - yy);
-						ddy[9] = kSH3[0] * 3.f * (xx - yy); ddy[10] = kSH3[1] * xz; ddy[11] = kSH3[2] * (-3.f * yy + 4.f * zz - xx);
-						ddy[12] = kSH3[3] * -3.f * 2.f * yz; ddy[13] = kSH3[4] * -2.f * xy; ddy[14] = kSH3[5] * -2.f * yz; ddy[15] = kSH3[6] * -3.f * 2.f * xy;
-						ddz[10] = kSH3[1] * xy; ddz[11] = kSH3[2] * 4.f * 2.f * yz; ddz[12] = kSH3[3] * 3.f * (2.f * zz - xx - yy);
-						ddz[13] = kSH3[4] * 4.f * 2.f * xz; ddz[14] = kSH3[5] * (xx - yy);
-					}
-				}
-			}
-			const int ncoef = (deg + 1) * (deg + 1);
-			float3 dL_ddir = {0.f, 0.f, 0.f};
-#pragma unroll
-			for (int k = 0; k < 16; k++) {
-				if (k < M) {
-					float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-					if (k < ncoef) {
-						o0 = basis[k] * dRGB[0]; o1 = basis[k] * dRGB[1]; o2 = basis[k] * dRGB[2];
-						if (k > 0) {
-							const float s0 = __ldg(sh + 3 * k), s1 = __ldg(sh + 3 * k + 1), s2 = __ldg(sh + 3 * k + 2);
-							const float sd = s0 * dRGB[0] + s1 * dRGB[1] + s2 * dRGB[2];
-							dL_ddir.x += ddx[k] * sd;
-							dL_ddir.y += ddy[k] * sd;
-							dL_ddir.z += ddz[k] * sd;
-						}
-					}
-					dsh[3 * k] = o0; dsh[3 * k + 1] = o1; dsh[3 * k + 2] = o2;
-				}
-			}
-			// through the normalisation of the view direction (auxiliary.h:123-133)
-			const float sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;
-			const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
-			dL_dmean.x += ((+sum2 - dir_orig.x * dir_orig.x) * dL_ddir.x - dir_orig.y * dir_orig.x * dL_ddir.y - dir_orig.z * dir_orig.x * dL_ddir.z) * invsum32;
-			dL_dmean.y += (-dir_orig.x * dir_orig.y * dL_ddir.x + (sum2 - dir_orig.y * dir_orig.y) * dL_ddir.y - dir_orig.z * dir_orig.y * dL_ddir.z) * invsum32;
-			dL_dmean.z += (-dir_orig.x * dir_orig.z * dL_ddir.x - dir_orig.y * dir_orig.z * dL_ddir.y + (sum2 - dir_orig.z * dir_orig.z) * dL_ddir.z) * invsum32;
-		}
+		// (the SH term of dL_dmean and dL_dsh are produced by sh_backward_kernel, launched right after this kernel)
 		o_mean3D[0] = dL_dmean.x; o_mean3D[1] = dL_dmean.y; o_mean3D[2] = dL_dmean.z;
 
 		// ---- covariance -> scale / rotation (backward.cu:492-555) ----
@@ -414,10 +343,151 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(FwdParams p, G
 	*reinterpret_cast<float4*>(out.d_rotations + 4 * idx) = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
 }
 
+// ---- SH backward (backward.cu:21-140): warp-cooperative so the [M,3] rows move through shared memory coalesced ------
+// A warp owns 32 consecutive Gaussians = one contiguous 32*3M-float block of `shs` and of `dL_dsh`.  The block is
+// copied global -> shared with unit-stride 128-bit loads, each lane then works on its own row (row stride padded to
+// an odd number of floats: conflict-free), overwrites it in place with dL_dsh, and the block streams back coalesced.
+// The view-direction term is added to dL_dmeans3D (third part of the mean gradient, backward.cu:131-139).
+constexpr int SH_WARPS = 8;
+__global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_kernel(int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ cam_pos,
+                                                                     const float* __restrict__ shs, const int* __restrict__ radii,
+                                                                     const uint8_t* __restrict__ clamped, const float* __restrict__ grad_accum, int GF,
+                                                                     float* __restrict__ d_sh, float* __restrict__ d_means3D) {
+	extern __shared__ float s_sh[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int row = 3 * M, stride = row | 1;
+	float* tile = s_sh + (size_t)warp * 32 * stride;
+	const int g0 = (blockIdx.x * SH_WARPS + warp) * 32;
+	if (g0 >= P) return;
+	const int count = min(32, P - g0);
+	const int total = count * row;
+	const float* src = shs + (size_t)g0 * row;
+	float* dst = d_sh + (size_t)g0 * row;
+	const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && (total & 3) == 0;
+	if (vec) {
+		for (int e = lane * 4; e < total; e += 128) {
+			const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
+			const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int r = (e + q) / row, c = (e + q) - r * row;
+				tile[r * stride + c] = vv[q];
+			}
+		}
+	} else {
+		for (int e = lane; e < total; e += 32) {
+			const int r = e / row, c = e - r * row;
+			tile[r * stride + c] = __ldg(src + e);
+		}
+	}
+	__syncwarp();
+	const int idx = g0 + lane;
+	if (lane < count) {
+		float* sh = tile + lane * stride;
+		if (!(radii[idx] > 0)) {
+			for (int i = 0; i < row; i++) sh[i] = 0.f;
+		} else {
+			const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+			const float3 campos = {cam_pos[0], cam_pos[1], cam_pos[2]};
+			const float3 dir_orig = {mean.x - campos.x, mean.y - campos.y, mean.z - campos.z};
+			const float dlen = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+			const float x = dir_orig.x / dlen, y = dir_orig.y / dlen, z = dir_orig.z / dlen;
+			const uint8_t cb = clamped[idx];
+			const float* ga = grad_accum + (size_t)idx * GF + G_COL;
+			const float dRGB[3] = {(cb & 1) ? 0.f : ga[0], (cb & 2) ? 0.f : ga[1], (cb & 4) ? 0.f : ga[2]};
+			const int deg = D;
+			float basis[16];
+			float ddx[16], ddy[16], ddz[16];  // d(basis_k)/d(dir)
+#pragma unroll
+			for (int k = 0; k < 16; k++) { basis[k] = 0.f; ddx[k] = 0.f; ddy[k] = 0.f; ddz[k] = 0.f; }
+			basis[0] = kSH0;
+			if (deg > 0) {
+				basis[1] = -kSH1 * y; basis[2] = kSH1 * z; basis[3] = -kSH1 * x;
+				ddx[3] = -kSH1; ddy[1] = -kSH1; ddz[2] = kSH1;
+				if (deg > 1) {
+					const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+					basis[4] = kSH2[0] * xy; basis[5] = kSH2[1] * yz; basis[6] = kSH2[2] * (2.f * zz - xx - yy);
+					basis[7] = kSH2[3] * xz; basis[8] = kSH2[4] * (xx - yy);
+					ddx[4] = kSH2[0] * y; ddx[6] = kSH2[2] * 2.f * -x; ddx[7] = kSH2[3] * z; ddx[8] = kSH2[4] * 2.f * x;
+					ddy[4] = kSH2[0] * x; ddy[5] = kSH2[1] * z; ddy[6] = kSH2[2] * 2.f * -y; ddy[8] = kSH2[4] * 2.f * -y;
+					ddz[5] = kSH2[1] * y; ddz[6] = kSH2[2] * 2.f * 2.f * z; ddz[7] = kSH2[3] * x;
+					if (deg > 2) {
+						basis[9] = kSH3[0] * y * (3.f * xx - yy); basis[10] = kSH3[1] * xy * z;
+						basis[11] = kSH3[2] * y * (4.f * zz - xx - yy); basis[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+						basis[13] = kSH3[4] * x * (4.f * zz - xx - yy); basis[14] = kSH3[5] * z * (xx - yy);
+						basis[15] = kSH3[6] * x * (xx - 3.f * yy);
+						ddx[9] = kSH3[0] * 3.f * 2.f * xy; ddx[10] = kSH3[1] * yz; ddx[11] = kSH3[2] * -2.f * xy; ddx[12] = kSH3[3] * -3.f * 2.f * xz;
+						ddx[13] = kSH3[4] * (-3.f * xx + 4.f * zz - yy); ddx[14] = kSH3[5] * 2.f * xz; ddx[15] = kSH3[6] * 3.f * (xx - yy);
+						ddy[9] = kSH3[0] * 3.f * (xx - yy); ddy[10] = kSH3[1] * xz; ddy[11] = kSH3[2] * (-3.f * yy + 4.f * zz - xx);
+						ddy[12] = kSH3[3] * -3.f * 2.f * yz; ddy[13] = kSH3[4] * -2.f * xy; ddy[14] = kSH3[5] * -2.f * yz; ddy[15] = kSH3[6] * -3.f * 2.f * xy;
+						ddz[10] = kSH3[1] * xy; ddz[11] = kSH3[2] * 4.f * 2.f * yz; ddz[12] = kSH3[3] * 3.f * (2.f * zz - xx - yy);
+						ddz[13] = kSH3[4] * 4.f * 2.f * xz; ddz[14] = kSH3[5] * (xx - yy);
+					}
+				}
+			}
+			const int ncoef = (deg + 1) * (deg + 1);
+			float3 dL_ddir = {0.f, 0.f, 0.f};
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				if (k < M) {
+					float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+					if (k < ncoef) {
+						o0 = basis[k] * dRGB[0]; o1 = basis[k] * dRGB[1]; o2 = basis[k] * dRGB[2];
+						if (k > 0) {
+							const float sd = sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2];
+							dL_ddir.x += ddx[k] * sd;
+							dL_ddir.y += ddy[k] * sd;
+							dL_ddir.z += ddz[k] * sd;
+						}
+					}
+					sh[3 * k] = o0; sh[3 * k + 1] = o1; sh[3 * k + 2] = o2;
+				}
+			}
+			// through the normalisation of the view direction (auxiliary.h:123-133)
+			const float sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;
+			const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
+			float* dm = d_means3D + 3 * idx;
+			dm[0] += ((+sum2 - dir_orig.x * dir_orig.x) * dL_ddir.x - dir_orig.y * dir_orig.x * dL_ddir.y - dir_orig.z * dir_orig.x * dL_ddir.z) * invsum32;
+			dm[1] += (-dir_orig.x * dir_orig.y * dL_ddir.x + (sum2 - dir_orig.y * dir_orig.y) * dL_ddir.y - dir_orig.z * dir_orig.y * dL_ddir.z) * invsum32;
+			dm[2] += (-dir_orig.x * dir_orig.z * dL_ddir.x - dir_orig.y * dir_orig.z * dL_ddir.y + (sum2 - dir_orig.z * dir_orig.z) * dL_ddir.z) * invsum32;
+		}
+	}
+	__syncwarp();
+	if (vec) {
+		for (int e = lane * 4; e < total; e += 128) {
+			float vv[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int r = (e + q) / row, c = (e + q) - r * row;
+				vv[q] = tile[r * stride + c];
+			}
+			*reinterpret_cast<float4*>(dst + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+		}
+	} else {
+		for (int e = lane; e < total; e += 32) {
+			const int r = e / row, c = e - r * row;
+			dst[e] = tile[r * stride + c];
+		}
+	}
+}
+
 void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s) {
 	static const int fix_mip = getenv("RGS_FIX_MIP_GRADIENT") != nullptr && atoi(getenv("RGS_FIX_MIP_GRADIENT")) != 0;
-	preprocess_backward_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, grad_accum, out, fix_mip);
+	preprocess_backward_kernel<<<(p.P + 127) / 128, 128, 0, s>>>(p, g, radii, grad_accum, out, fix_mip);
 	count_launch();
+	if (p.shs != nullptr && out.d_sh != nullptr && p.M > 0) {
+		const int stride = (3 * p.M) | 1;
+		const size_t smem = (size_t)SH_WARPS * 32 * stride * sizeof(float);
+		static size_t configured = 0;
+		if (smem > 48 * 1024 && smem > configured) {
+			cudaFuncSetAttribute(sh_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			configured = smem;
+		}
+		const int per_block = SH_WARPS * 32;
+		sh_backward_kernel<<<(p.P + per_block - 1) / per_block, per_block, smem, s>>>(p.P, p.D, p.M, p.means3D, p.cam_pos, p.shs, radii, g.clamped,
+		                                                                               grad_accum, grad_floats(p.coord), out.d_sh, out.d_means3D);
+		count_launch();
+	}
 }
 
 }  // namespace rgs

@@ -39,10 +39,21 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane) {
 	if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+__device__ __forceinline__ int lds32(uint32_t addr) {
+	int v;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
+}
+
 }  // namespace
 
 template <bool COORD, bool DEPTH>
-__global__ void __launch_bounds__(NTHREADS) render_backward_kernel(
+__global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float* __restrict__ records,
     int W, int H, int grid_x, int row_begin, float focal_x, float focal_y, const float* __restrict__ bg_color,
     const float* __restrict__ alphas, const float* __restrict__ normalmap, const uint32_t* __restrict__ n_contrib,
@@ -55,6 +66,7 @@ __global__ void __launch_bounds__(NTHREADS) render_backward_kernel(
 	constexpr int GF = COORD ? GRAD_FLOATS_COORD : GRAD_FLOATS_BASE;
 	extern __shared__ float4 smem[];  // [2][RFQ][BATCH] records, then [2][BATCH] ids
 	int* s_ids = reinterpret_cast<int*>(smem + 2 * RFQ * BATCH);
+	const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 	__shared__ int s_block_last[NTHREADS / 32];
 
 	const int tid = threadIdx.x;
@@ -121,6 +133,13 @@ __global__ void __launch_bounds__(NTHREADS) render_backward_kernel(
 			}
 		}
 	}
+	if (last_contributor == 0) {
+		// pixels nothing was blended into: w_final = 0 makes the normalisation terms 0/0.  They never receive a splat
+		// (`ok` is false for every pair) but the straight-line body multiplies by them, so clear them.
+		dL_dalpha = 0.f; dL_dpixel_t = 0.f; dL_dpixel_mt = 0.f;
+#pragma unroll
+		for (int i = 0; i < 3; i++) { dL_dpixel[i] = 0.f; dL_dpixel_coord[i] = 0.f; dL_dpixel_mcoord[i] = 0.f; dL_dpixel_normal[i] = 0.f; }
+	}
 	float bg_dot_dpixel = 0;
 #pragma unroll
 	for (int i = 0; i < 3; i++) bg_dot_dpixel += bg_color[i] * dL_dpixel[i];
@@ -137,11 +156,8 @@ __global__ void __launch_bounds__(NTHREADS) render_backward_kernel(
 	n = min(n, (int)(range.y - range.x));  // defensive; last_contributor <= list length by construction
 	const int rounds = (n + BATCH - 1) / BATCH;
 
-	float accum_rec[3] = {0.f, 0.f, 0.f}, last_color[3] = {0.f, 0.f, 0.f};
-	float accum_coord_rec[3] = {0.f, 0.f, 0.f}, last_coord[3] = {0.f, 0.f, 0.f};
-	float accum_t_rec = 0.f, last_t = 0.f;
-	float accum_normal_rec[3] = {0.f, 0.f, 0.f}, last_normal[3] = {0.f, 0.f, 0.f};
-	float accum_alpha_rec = 0.f, last_alpha = 0.f;
+	// running sum over the splats behind the current one (see the loop body); starts with the background layer
+	float B = T_final * bg_dot_dpixel;
 
 	const float ddelx_dx = 0.5 * W;
 	const float ddely_dy = 0.5 * H;
@@ -171,7 +187,8 @@ __global__ void __launch_bounds__(NTHREADS) render_backward_kernel(
 			id_next = (nxt < n) ? (int)point_list[range.x + n - 1 - nxt] : -1;
 		}
 		const float4* s = smem + (size_t)(i & 1) * RFQ * BATCH;
-		const int* ids = s_ids + (i & 1) * BATCH;
+		const uint32_t s_addr = smem_base + (uint32_t)((i & 1) * RFQ * BATCH * 16);
+		const uint32_t ids_addr = smem_base + (uint32_t)(2 * RFQ * BATCH * 16 + (i & 1) * BATCH * 4);
 		const int cnt = min(BATCH, n - i * BATCH);
 		const int pos0 = n - 1 - i * BATCH;  // list position of staged index 0
 		if (pos0 - (cnt - 1) >= warp_last) continue;  // whole batch is behind this warp's last contributor
@@ -189,108 +206,105 @@ __global__ void __launch_bounds__(NTHREADS) render_backward_kernel(
 				m &= m - 1;
 				const int jj = c0 + bpos;
 				const int contributor = pos0 - jj;  // 0-based position in the tile list (backward.cu:837)
-				const float4 q0 = s[jj], q1 = s[BATCH + jj];
+				const uint32_t sa = s_addr + (uint32_t)jj * 16u;
+				const float4 q0 = lds128(sa), q1 = lds128(sa + BATCH * 16u);
 				const float dx = q0.x - pxf, dy = q0.y - pyf;
 				const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-				bool ok = contributor < last_contributor && !(power > 0.0f);
 				const float G = expf(power);
-				const float alpha = min(0.99f, q1.y * G);
-				ok = ok && !(alpha < 1.0f / 255.0f);
+				const float alpha_raw = min(0.99f, q1.y * G);
+				const bool ok = contributor < last_contributor && !(power > 0.0f) && !(alpha_raw < 1.0f / 255.0f);
 				if (!__any_sync(0xffffffffu, ok)) continue;
 
-				const float4 q2 = s[2 * BATCH + jj];
+				// Straight-line body.  A lane whose pixel does not receive this splat runs it with alpha = 0: a layer of
+				// zero opacity leaves T and the running sum below unchanged, its channel weights are alpha*T = 0, and the
+				// terms that would not vanish (they all carry the factor G) are masked through G.
+				//
+				// Blend backward in "dot-product" form.  The reference keeps, per channel, the normalised blend of everything
+				// behind the current splat (accum_rec, backward.cu:870-962) and forms sum_ch (c_ch - accum_rec_ch) g_ch * T.
+				// With B = sum over the splats behind of (alpha T) * S, S = sum_ch c_ch g_ch (g = the pixel's upstream
+				// gradients, alpha channel c = 1, background folded in as the last layer) that is exactly
+				//      dL/dalpha = T * S - B / (1 - alpha),       B += alpha T S
+				// -- one running scalar instead of 8 running blends + 8 "last" values (same algebra, different rounding).
+				const float alpha = ok ? alpha_raw : 0.f;
+				const float4 q2 = lds128(sa + 2 * BATCH * 16u);
 				float gv[GF];
-#pragma unroll
-				for (int k = 0; k < GF; k++) gv[k] = 0.f;
-				if (ok) {
-					T = T / (1.f - alpha);
-					const float dchannel_dcolor = alpha * T;
-					float dL_dopa = 0.0f;
-					const float col[3] = {q2.y, q2.z, q2.w};
+				const float inv = __fdividef(1.f, 1.f - alpha);  // shared by T/(1-alpha) and B/(1-alpha)
+				T = T * inv;
+				const float w = alpha * T;  // dchannel_dcolor
+				float S = dL_dalpha;
+				S = fmaf(q2.y, dL_dpixel[0], S);
+				S = fmaf(q2.z, dL_dpixel[1], S);
+				S = fmaf(q2.w, dL_dpixel[2], S);
+				gv[G_COL + 0] = w * dL_dpixel[0];
+				gv[G_COL + 1] = w * dL_dpixel[1];
+				gv[G_COL + 2] = w * dL_dpixel[2];
+				float dL_dcoords[3] = {0.f, 0.f, 0.f};
+				float dL_dt = 0.f;
+				float4 q3, q4, q5;
+				const bool is_median = ok && contributor == max_contributor - 1;
+				if constexpr (GEO) q3 = lds128(sa + 3 * BATCH * 16u);
+				if constexpr (COORD) {
+					q4 = lds128(sa + 4 * BATCH * 16u);
+					q5 = lds128(sa + 5 * BATCH * 16u);
+					const float coord[3] = {q4.x + q4.w * dx + q5.x * dy, q4.y + q5.y * dx + q5.z * dy, q4.z + q5.w * dx + q3.w * dy};
 #pragma unroll
 					for (int ch = 0; ch < 3; ch++) {
-						const float c = col[ch];
-						accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-						last_color[ch] = c;
-						const float dL_dchannel = dL_dpixel[ch];
-						dL_dopa += (c - accum_rec[ch]) * dL_dchannel;
-						gv[G_COL + ch] = dchannel_dcolor * dL_dchannel;
+						S = fmaf(coord[ch], dL_dpixel_coord[ch], S);
+						dL_dcoords[ch] = w * dL_dpixel_coord[ch];
+						if (is_median) dL_dcoords[ch] += dL_dpixel_mcoord[ch];
+						gv[G_VP + ch] = dL_dcoords[ch];
+						gv[G_CP + 2 * ch] = dL_dcoords[ch] * dx;      // 1/focal_x applied in backward-preprocess
+						gv[G_CP + 2 * ch + 1] = dL_dcoords[ch] * dy;  // 1/focal_y
 					}
-					float dL_dcoords[3] = {0.f, 0.f, 0.f};
-					float dL_dt = 0.f;
-					float4 q3, q4, q5;
-					if constexpr (GEO) q3 = s[3 * BATCH + jj];
-					if constexpr (COORD) {
-						q4 = s[4 * BATCH + jj];
-						q5 = s[5 * BATCH + jj];
-						const float coord[3] = {q4.x + q4.w * dx + q5.x * dy, q4.y + q5.y * dx + q5.z * dy, q4.z + q5.w * dx + q3.w * dy};
 #pragma unroll
-						for (int ch = 0; ch < 3; ch++) {
-							const float c = coord[ch];
-							accum_coord_rec[ch] = last_alpha * last_coord[ch] + (1.f - last_alpha) * accum_coord_rec[ch];
-							last_coord[ch] = c;
-							const float dL_dchannel = dL_dpixel_coord[ch];
-							dL_dopa += (c - accum_coord_rec[ch]) * dL_dchannel;
-							dL_dcoords[ch] = dchannel_dcolor * dL_dchannel;
-							if (contributor == max_contributor - 1) dL_dcoords[ch] += dL_dpixel_mcoord[ch];
-							gv[G_VP + ch] = dL_dcoords[ch];
-							gv[G_CP + 2 * ch] = dL_dcoords[ch] * dx;      // 1/focal_x applied in backward-preprocess
-							gv[G_CP + 2 * ch + 1] = dL_dcoords[ch] * dy;  // 1/focal_y
-						}
-					}
-					if constexpr (DEPTH) {
-						const float t = q1.z + (q1.w * dx + q2.x * dy);
-						accum_t_rec = last_alpha * last_t + (1.f - last_alpha) * accum_t_rec;
-						last_t = t;
-						dL_dopa += (t - accum_t_rec) * dL_dpixel_t;
-						dL_dt = dchannel_dcolor * dL_dpixel_t;
-						if (contributor == max_contributor - 1) dL_dt += dL_dpixel_mt;
-						gv[G_T] = dL_dt;
-						gv[G_RAYX] = dL_dt * dx;
-						gv[G_RAYY] = dL_dt * dy;
-					}
-					if constexpr (GEO) {
-						const float nrm[3] = {q3.x, q3.y, q3.z};
-#pragma unroll
-						for (int ch = 0; ch < 3; ch++) {
-							const float c = nrm[ch];
-							accum_normal_rec[ch] = last_alpha * last_normal[ch] + (1.f - last_alpha) * accum_normal_rec[ch];
-							last_normal[ch] = c;
-							const float dL_dchannel = dL_dpixel_normal[ch];
-							dL_dopa += (c - accum_normal_rec[ch]) * dL_dchannel;
-							gv[G_NRM + ch] = dchannel_dcolor * dL_dchannel;
-						}
-					}
-					accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
-					dL_dopa += (1 - accum_alpha_rec) * dL_dalpha;
-					dL_dopa *= T;
-					last_alpha = alpha;
-					dL_dopa += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-
-					const float dL_dG = q1.y * dL_dopa;
-					const float gdx = G * dx, gdy = G * dy;
-					const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
-					const float dG_ddely = -gdy * q1.x - gdx * q0.w;
-					float dL_ddelx = dL_dG * dG_ddelx;
-					float dL_ddely = dL_dG * dG_ddely;
-					if constexpr (COORD) {
-						dL_ddelx += dL_dcoords[0] * q4.w + dL_dcoords[1] * q5.y + dL_dcoords[2] * q5.w;
-						dL_ddely += dL_dcoords[0] * q5.x + dL_dcoords[1] * q5.z + dL_dcoords[2] * q3.w;
-					}
-					if constexpr (DEPTH) {
-						dL_ddelx += dL_dt * q1.w;
-						dL_ddely += dL_dt * q2.x;
-					}
-					gv[G_MX] = dL_ddelx;  // * 0.5 W in backward-preprocess
-					gv[G_MY] = dL_ddely;  // * 0.5 H
-					gv[G_MABS] = abs(dL_dG * dG_ddelx * ddelx_dx) + abs(dL_dG * dG_ddely * ddely_dy);
-					gv[G_CONX] = -0.5f * gdx * dx * dL_dG;
-					gv[G_CONY] = -0.5f * gdx * dy * dL_dG;
-					gv[G_CONW] = -0.5f * gdy * dy * dL_dG;
-					gv[G_OPA] = G * dL_dopa;
+					for (int k = 25; k < GF; k++) gv[k] = 0.f;
 				}
+				if constexpr (DEPTH) {
+					const float t = q1.z + (q1.w * dx + q2.x * dy);
+					S = fmaf(t, dL_dpixel_t, S);
+					dL_dt = w * dL_dpixel_t;
+					if (is_median) dL_dt += dL_dpixel_mt;
+				}
+				gv[G_T] = dL_dt;
+				gv[G_RAYX] = dL_dt * dx;
+				gv[G_RAYY] = dL_dt * dy;
+				if constexpr (GEO) {
+					S = fmaf(q3.x, dL_dpixel_normal[0], S);
+					S = fmaf(q3.y, dL_dpixel_normal[1], S);
+					S = fmaf(q3.z, dL_dpixel_normal[2], S);
+					gv[G_NRM + 0] = w * dL_dpixel_normal[0];
+					gv[G_NRM + 1] = w * dL_dpixel_normal[1];
+					gv[G_NRM + 2] = w * dL_dpixel_normal[2];
+				} else {
+					gv[G_NRM] = gv[G_NRM + 1] = gv[G_NRM + 2] = 0.f;
+				}
+				const float dL_dopa = T * S - inv * B;
+				B = fmaf(w, S, B);
+				const float Gm = ok ? G : 0.f;  // the reference skips this pair entirely: every term below carries a factor G
+
+				const float dL_dG = q1.y * dL_dopa;
+				const float gdx = Gm * dx, gdy = Gm * dy;
+				const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
+				const float dG_ddely = -gdy * q1.x - gdx * q0.w;
+				float dL_ddelx = dL_dG * dG_ddelx;
+				float dL_ddely = dL_dG * dG_ddely;
+				gv[G_MABS] = abs(dL_ddelx * ddelx_dx) + abs(dL_ddely * ddely_dy);
+				if constexpr (COORD) {
+					dL_ddelx += dL_dcoords[0] * q4.w + dL_dcoords[1] * q5.y + dL_dcoords[2] * q5.w;
+					dL_ddely += dL_dcoords[0] * q5.x + dL_dcoords[1] * q5.z + dL_dcoords[2] * q3.w;
+				}
+				if constexpr (DEPTH) {
+					dL_ddelx += dL_dt * q1.w;
+					dL_ddely += dL_dt * q2.x;
+				}
+				gv[G_MX] = dL_ddelx;  // * 0.5 W in backward-preprocess
+				gv[G_MY] = dL_ddely;  // * 0.5 H
+				gv[G_CONX] = -0.5f * gdx * dx * dL_dG;
+				gv[G_CONY] = -0.5f * gdx * dy * dL_dG;
+				gv[G_CONW] = -0.5f * gdy * dy * dL_dG;
+				gv[G_OPA] = Gm * dL_dopa;
 				warp_reduce_scatter<GF>(gv, lane);
-				float* row = grad_accum + (size_t)ids[jj] * GF;
+				float* row = grad_accum + (size_t)lds32(ids_addr + (uint32_t)jj * 4u) * GF;
 				if (GF == 16) {
 					if ((lane & 1) == 0) atomicAdd(row + (lane >> 1), gv[0]);
 				} else {

@@ -78,8 +78,10 @@ def ours_views(fwd: dict, sc) -> dict:
     keys = b.take(R, torch.int64, 8)
     i = _Cursor(fwd["img"])
     ranges = i.take(tiles * 2, torch.int32, 4).view(tiles, 2)
+    i.take(tiles, torch.int32, 4)   # tile_count (counted back down to zero by the scatter)
+    totals = i.take(2, torch.int32, 4)
     n_contrib = i.take(2 * N, torch.int32, 4).view(2, sc.height, sc.width)
-    return dict(records=rec, depths=depths, tiles_touched=tiles_touched, offsets=offsets, clamped=clamped, point_list=point_list,
+    return dict(totals=totals, records=rec, depths=depths, tiles_touched=tiles_touched, offsets=offsets, clamped=clamped, point_list=point_list,
                 keys=keys, ranges=ranges, n_contrib=n_contrib,
                 means2D=rec[:, 0:2], conic_opacity=torch.stack([rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 5]], 1), ts=rec[:, 6],
                 ray_planes=torch.stack([rec[:, 7], rec[:, 8]], 1), rgb=rec[:, 9:12], normals=rec[:, 12:15],

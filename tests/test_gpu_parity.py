@@ -236,4 +236,6 @@ def test_c2_slabs_compose_to_the_whole(c2):
     from rade_gs_b200 import rawapi
     whole = rawapi.backward(C, sc, f, g)
     for k, o in zip(GRAD_KEYS, out):
-        grad_close_gpu(o.cpu().numpy(), whole[k].cpu().numpy(), k)  # float-atomic summation order differs between the two paths
+        # float-atomic summation order differs between the two paths; at 1M splats a handful of ill-conditioned splats
+        # amplify that to ~2e-3 of the tensor maximum (the reference's own run-to-run spread is 1.6e-3 here)
+        grad_close_gpu(o.cpu().numpy(), whole[k].cpu().numpy(), k, rel=1e-3, elem=1e-2)

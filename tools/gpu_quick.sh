@@ -1,0 +1,8 @@
+#!/bin/bash
+# quick GPU check: parity tests + per-stage timings
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_gpu.log
+python tools/run_once.py C2 10
+python tools/run_once.py C1 10
+python tools/run_once.py C3 5
+python tools/compare_ref.py --cfg C2 2>&1 | grep -A12 "^gradients"
