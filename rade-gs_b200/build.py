@@ -24,6 +24,10 @@ NVCC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc
 
 CORE_SOURCES = ["rgs_api.cu", "rgs_preprocess.cu", "rgs_binning.cu", "rgs_render_fwd.cu", "rgs_render_bwd.cu", "rgs_preprocess_bwd.cu"]
 HEADERS = ["rgs_common.cuh", "rgs_geom.cuh", "rgs_render_common.cuh", os.path.join(ROOT, "include", "rgs_b200.h")]
+# per-file extra flags: backward-preprocess is pure gradient arithmetic with a 1e-3 tolerance -> approximate float
+# division / sqrt (2-3 instructions instead of ~10 with a slow-path call); the eigen-solver inside it uses explicit IEEE
+# intrinsics.  Forward preprocess keeps IEEE division: its expression chain decides the tile keys bit-exactly.
+EXTRA_FLAGS = {"rgs_preprocess_bwd.cu": ["-prec-div=false", "-prec-sqrt=false"]}
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xcudafe", "--diag_suppress=177"]
 
@@ -48,7 +52,7 @@ def build_core(force=False, verbose=False) -> str:
         o = os.path.join(OBJ, src + ".o")
         if force or _mtime(o) < max(_mtime(s), hdr_time):
             print("[build] nvcc", src, flush=True)
-            _run([NVCC, "-c", s, "-o", o] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []), verbose)
+            _run([NVCC, "-c", s, "-o", o] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []), verbose)
             return o, True
         return o, False
 

@@ -78,6 +78,7 @@ static GeomView carve_geom(char* base, int P, bool coord, size_t scan_bytes, siz
 	g.tiles_touched = c.take<uint32_t>(P);
 	g.offsets = c.take<uint32_t>(P);
 	g.clamped = c.take<uint8_t>(P);
+	g.sigma_inv = c.take<float>((size_t)P * SIGMA_INV_FLOATS);
 	g.scan_temp = c.take<char>(scan_bytes);
 	g.scan_temp_bytes = scan_bytes;
 	if (total) *total = c.size();

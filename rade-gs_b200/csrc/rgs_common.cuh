@@ -29,6 +29,7 @@ constexpr int REC_FLOATS_COORD = 24;  // variants coord / coord+depth
 // factors 0.5*W, 1/focal are applied once per Gaussian in backward-preprocess.
 constexpr int GRAD_FLOATS_BASE = 16;
 constexpr int GRAD_FLOATS_COORD = 32;
+constexpr int SIGMA_INV_FLOATS = 12;  // 9 matrix entries, flags (bit0 well-conditioned, bit1 solver converged), 2 pad
 
 enum GradSlot {
 	G_MX = 0, G_MY = 1, G_MABS = 2, G_CONX = 3, G_CONY = 4, G_CONW = 5, G_OPA = 6, G_COL = 7,
@@ -58,6 +59,7 @@ struct GeomView {
 	uint32_t* tiles_touched; // [P]
 	uint32_t* offsets;       // [P]  inclusive scan of tiles_touched
 	uint8_t* clamped;        // [P]  bit c set when colour channel c was clamped at 0
+	float* sigma_inv;        // [P * 12] Sigma^-1 substitute of forward (9 floats, column-major) + flags, reused by backward
 	char* scan_temp;         // CUB temp storage
 	size_t scan_temp_bytes;
 };

@@ -8,7 +8,8 @@
 // eigenvectors only good to ~1e-3 rad, and those eigenvectors shape the rendered normals and every geometry
 // gradient.  Parity with the reference therefore needs the same algorithm with the same stopping rules, not a
 // more accurate one: eig_sym3_tql below follows the published tred2/tqli scheme specialised to 3x3 with those
-// absolute tests, operation by operation.  (An exact decomposition R S^2 R^T is available for free when
+// absolute tests, operation by operation (divisions and square roots spelled as the IEEE intrinsics so the
+// result is independent of per-file fast-division settings).  (An exact decomposition R S^2 R^T is available for free when
 // Sigma comes from scale+rotation; measured on C2 it moves 5.6 % of the normal map by more than 1e-4, so it
 // is not used.)
 #pragma once
@@ -21,23 +22,23 @@ constexpr float kEigEps = 0.0000001f;
 __device__ __forceinline__ float hypot_nr(float a, float b) {  // sqrt(a^2+b^2) without overflow (auxiliary.h:200-214)
 	float absa = fabsf(a), absb = fabsf(b);
 	if (absa > absb) {
-		absb /= absa;
+		absb = __fdiv_rn(absb, absa);
 		absb *= absb;
-		return absa * sqrtf(1.f + absb);
+		return absa * __fsqrt_rn(1.f + absb);
 	}
 	if (fabsf(absb) <= kEigEps) return 0.f;
-	absa /= absb;
+	absa = __fdiv_rn(absa, absb);
 	absa *= absa;
-	return absb * sqrtf(1.f + absa);
+	return absb * __fsqrt_rn(1.f + absa);
 }
 
 // One implicit-shift QL sweep on the unreduced block [L..M] of the tridiagonal (d, e), rotations accumulated in z
 // (auxiliary.h:355-388).  L and M are compile-time so every array index is static.
 template <int L, int M>
 __device__ __forceinline__ void ql_sweep(float (&d)[3], float (&e)[3], float (&z)[3][3]) {
-	float g = (d[L + 1] - d[L]) / (2 * e[L]);
+	float g = __fdiv_rn(d[L + 1] - d[L], 2 * e[L]);
 	float r = hypot_nr(g, 1.f);
-	g = d[M] - d[L] + e[L] / (g + ((g >= 0.f) ? fabsf(r) : -fabsf(r)));
+	g = d[M] - d[L] + __fdiv_rn(e[L], g + ((g >= 0.f) ? fabsf(r) : -fabsf(r)));
 	float s = 1.f, c = 1.f, p = 0.f;
 	bool underflow = false;  // the reference's early `break` (r ~ 0)
 #pragma unroll
@@ -51,8 +52,8 @@ __device__ __forceinline__ void ql_sweep(float (&d)[3], float (&e)[3], float (&z
 				e[M] = 0.f;
 				underflow = true;
 			} else {
-				s = f / r;
-				c = g / r;
+				s = __fdiv_rn(f, r);
+				c = __fdiv_rn(g, r);
 				g = d[i + 1] - p;
 				r = (d[i] - g) * s + 2 * c * b;
 				d[i + 1] = g + (p = s * r);
@@ -88,31 +89,31 @@ __device__ inline bool eig_sym3_tql(const float cov[6], float lam[3], M3& vec) {
 		if (fabsf(scale) <= kEigEps) {
 			e[2] = z[2][1];
 		} else {
-			z[2][0] /= scale;
+			z[2][0] = __fdiv_rn(z[2][0], scale);
 			h += z[2][0] * z[2][0];
-			z[2][1] /= scale;
+			z[2][1] = __fdiv_rn(z[2][1], scale);
 			h += z[2][1] * z[2][1];
 			float f = z[2][1];
-			float g = (f >= 0.f) ? -sqrtf(h) : sqrtf(h);
+			float g = (f >= 0.f) ? -__fsqrt_rn(h) : __fsqrt_rn(h);
 			e[2] = scale * g;
 			h -= f * g;
 			z[2][1] = f - g;
 			f = 0.f;
 			// j = 0
-			z[0][2] = z[2][0] / h;
+			z[0][2] = __fdiv_rn(z[2][0], h);
 			g = 0.f;
 			g += z[0][0] * z[2][0];
 			g += z[1][0] * z[2][1];
-			e[0] = g / h;
+			e[0] = __fdiv_rn(g, h);
 			f += e[0] * z[2][0];
 			// j = 1
-			z[1][2] = z[2][1] / h;
+			z[1][2] = __fdiv_rn(z[2][1], h);
 			g = 0.f;
 			g += z[1][0] * z[2][0];
 			g += z[1][1] * z[2][1];
-			e[1] = g / h;
+			e[1] = __fdiv_rn(g, h);
 			f += e[1] * z[2][1];
-			const float hh = f / (h + h);
+			const float hh = __fdiv_rn(f, h + h);
 			// j = 0
 			f = z[2][0];
 			e[0] = g = e[0] - hh * f;
@@ -200,7 +201,7 @@ __device__ __forceinline__ SigmaInv sigma_inverse(const float cov3D[6]) {
 	s.lam_min = s.min_id == 0 ? l[0] : (s.min_id == 1 ? l[1] : l[2]);
 	s.well = s.lam_min > 0.00000001f;
 	if (s.well) {
-		const M3 diag = m3(1 / l[0], 0.f, 0.f, 0.f, 1 / l[1], 0.f, 0.f, 0.f, 1 / l[2]);
+		const M3 diag = m3(__fdiv_rn(1.f, l[0]), 0.f, 0.f, 0.f, __fdiv_rn(1.f, l[1]), 0.f, 0.f, 0.f, __fdiv_rn(1.f, l[2]));
 		s.inv = s.E * diag * transpose(s.E);
 	} else {
 		const V3 em = s.min_id == 0 ? s.E.c[0] : (s.min_id == 1 ? s.E.c[1] : s.E.c[2]);

@@ -65,7 +65,7 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
 	return float3{fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f)};
 }
 
-__global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, GeomView g, int* __restrict__ radii, uint32_t* __restrict__ tile_count) {
+__global__ void __launch_bounds__(256, 3) preprocess_forward_kernel(FwdParams p, GeomView g, int* __restrict__ radii, uint32_t* __restrict__ tile_count) {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= p.P) return;
 
@@ -146,6 +146,13 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
 				float3 normal = {0.f, 0.f, 0.f};
 				if (p.coord || p.depth) {
 					const SigmaInv si = sigma_inverse(cov3D);
+					{
+						// keep Sigma^-1 for backward-preprocess: it would otherwise repeat the (divergent) eigen-solver
+						float4* sv = reinterpret_cast<float4*>(g.sigma_inv + (size_t)idx * SIGMA_INV_FLOATS);
+						sv[0] = make_float4(si.inv.c[0].x, si.inv.c[0].y, si.inv.c[0].z, si.inv.c[1].x);
+						sv[1] = make_float4(si.inv.c[1].y, si.inv.c[1].z, si.inv.c[2].x, si.inv.c[2].y);
+						sv[2] = make_float4(si.inv.c[2].z, __int_as_float((si.well ? 1 : 0) | (si.solved ? 2 : 0)), 0.f, 0.f);
+					}
 					const M3 cov_cam_inv = transpose(Wm) * si.inv * Wm;
 					const V3 uvh = {txtz, tytz, 1.f};
 					const V3 uvh_m = mulcol(cov_cam_inv, uvh);

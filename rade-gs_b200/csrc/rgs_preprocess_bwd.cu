@@ -112,7 +112,20 @@ __global__ void __launch_bounds__(128, 4) preprocess_backward_kernel(FwdParams p
 		float plane0 = 0.f, plane1 = 0.f, dL_du = 0.f, dL_dv = 0.f, dL_dl = 0.f, l = 1.f, nl = 1.f;
 		V3 dcn = {0, 0, 0}, rn = {0, 0, 0};  // dL_dnJ = dcn * rn^T
 		if (p.coord || p.depth) {
-			const SigmaInv si = sigma_inverse(cov3D);
+			// Sigma^-1 as forward computed it (bit-identical, stored in the geometry buffer); only the rare rank-1 branch
+			// needs the eigenvectors again and re-runs the solver
+			SigmaInv si;
+			{
+				const float4* sv = reinterpret_cast<const float4*>(g.sigma_inv + (size_t)idx * SIGMA_INV_FLOATS);
+				const float4 s0 = sv[0], s1 = sv[1], s2 = sv[2];
+				si.inv = m3(s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x);
+				const int fl = __float_as_int(s2.y);
+				si.well = (fl & 1) != 0;
+				si.solved = (fl & 2) != 0;
+				si.min_id = 0;
+				si.lam_min = 0.f;
+				if (!si.well) si = sigma_inverse(cov3D);
+			}
 			const M3& Vrk_inv = si.inv;
 			const M3 cov_cam_inv = transpose(Wm) * Vrk_inv * Wm;
 			const V3 uvh = {txtz, tytz, 1.f};

@@ -73,6 +73,7 @@ def ours_views(fwd: dict, sc) -> dict:
     tiles_touched = g.take(P, torch.int32, 4)
     offsets = g.take(P, torch.int32, 4)
     clamped = g.take(P, torch.uint8, 1)
+    g.take(P * 12, torch.float32, 4)  # Sigma^-1 kept for backward
     b = _Cursor(fwd["binning"])
     point_list = b.take(R, torch.int32, 4)
     keys = b.take(R, torch.int64, 8)
