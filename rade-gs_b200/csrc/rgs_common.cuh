@@ -16,15 +16,17 @@ constexpr int TILE_Y = 16;
 constexpr int TILE_PIX = TILE_X * TILE_Y;
 
 // ---- packed per-Gaussian render record (written by preprocess, gathered by the render kernels) ----
-// floats: 0 mx 1 my 2 conic.x 3 conic.y | 4 conic.z 5 opacity*coef 6 t_center 7 ray.x |
-//         8 ray.y 9 r 10 g 11 b | 12 nx 13 ny 14 nz 15 cam_plane[5] |
+// floats: 0 mx 1 my 2 conic.x 3 conic.y | 4 conic.z 5 opacity*coef 6 ray.x 7 ray.y |
+//         8 r 9 g 10 b 11 t_center | 12 nx 13 ny 14 nz 15 cam_plane[5] |
 //         16 vx 17 vy 18 vz 19 cam_plane[0] | 20..23 cam_plane[1..4]
+// Pairs that are multiplied by a common factor in the blend sit in even/odd slots (mx,my), (ray.x,ray.y), (r,g),
+// (b,t), (nx,ny): they land in aligned register pairs and go through Blackwell's packed fp32x2 FMUL2/FFMA2.
 constexpr int REC_FLOATS_BASE = 16;   // variants none / depth
 constexpr int REC_FLOATS_COORD = 24;  // variants coord / coord+depth
 
 // ---- screen-space gradient accumulator (one row per Gaussian, written by backward-render) --------
-// floats: 0 dmx 1 dmy 2 |dm| 3 dconic.x 4 dconic.y 5 dconic.w(=yy) 6 dopacity 7..9 dcolor
-//         10 dt 11 dray.x 12 dray.y 13..15 dnormal | 16..18 dview_point 19..24 dcam_plane 25..31 pad
+// floats: 0 dmx 1 dmy | 2 dray.x 3 dray.y | 4 5 6 dcolor 7 dt | 8 9 10 dnormal 11 dopacity | 12 dconic.x 13 dconic.y
+//         14 dconic.w(=yy) 15 |dm|  ||  16..18 dview_point 19..24 dcam_plane 25..31 pad
 // mean2D / plane entries are stored UNSCALED (sum of dL/ddel, sum of dL_dt*d.x, ...): the constant
 // factors 0.5*W, 1/focal are applied once per Gaussian in backward-preprocess.
 constexpr int GRAD_FLOATS_BASE = 16;
@@ -32,8 +34,8 @@ constexpr int GRAD_FLOATS_COORD = 32;
 constexpr int SIGMA_INV_FLOATS = 12;  // 9 matrix entries, flags (bit0 well-conditioned, bit1 solver converged), 2 pad
 
 enum GradSlot {
-	G_MX = 0, G_MY = 1, G_MABS = 2, G_CONX = 3, G_CONY = 4, G_CONW = 5, G_OPA = 6, G_COL = 7,
-	G_T = 10, G_RAYX = 11, G_RAYY = 12, G_NRM = 13, G_VP = 16, G_CP = 19
+	G_MX = 0, G_MY = 1, G_RAYX = 2, G_RAYY = 3, G_COL = 4, G_T = 7, G_NRM = 8, G_OPA = 11, G_CONX = 12, G_CONY = 13, G_CONW = 14,
+	G_MABS = 15, G_VP = 16, G_CP = 19
 };
 
 __host__ __device__ inline int rec_floats(bool coord) { return coord ? REC_FLOATS_COORD : REC_FLOATS_BASE; }

@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(256, 3) preprocess_forward_kernel(FwdParams p,
 				const int RF = rec_floats(p.coord);
 				float4* rec = reinterpret_cast<float4*>(g.records + (size_t)idx * RF);
 				rec[0] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-				rec[1] = make_float4(conic.z, opac, ts, ray_plane.x);
-				rec[2] = make_float4(ray_plane.y, rgb.x, rgb.y, rgb.z);
+				rec[1] = make_float4(conic.z, opac, ray_plane.x, ray_plane.y);
+				rec[2] = make_float4(rgb.x, rgb.y, rgb.z, ts);
 				rec[3] = make_float4(normal.x, normal.y, normal.z, cam_plane[5]);
 				if (p.coord) {
 					rec[4] = make_float4(p_view.x, p_view.y, p_view.z, cam_plane[0]);

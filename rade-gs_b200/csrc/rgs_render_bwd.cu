@@ -27,14 +27,25 @@ template <int N>
 __device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane) {
 	static_assert(N == 16 || N == 32, "16 or 32 values");
 #pragma unroll
-	for (int h = N / 2, mask = 16; h >= 1; h >>= 1, mask >>= 1) {
+	for (int h = N / 2, mask = 16; h >= 2; h >>= 1, mask >>= 1) {
 		const bool upper = (lane & mask) != 0;
 #pragma unroll
-		for (int k = 0; k < h; k++) {
-			const float send = upper ? v[k] : v[k + h];
-			const float keep = upper ? v[k + h] : v[k];
-			v[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+		for (int k = 0; k < h; k += 2) {
+			// two values per step: the adds go through the packed fp32x2 pipe (one FADD2 instead of two FADD)
+			const float s0 = upper ? v[k] : v[k + h], s1 = upper ? v[k + 1] : v[k + h + 1];
+			const float2 keep = make_float2(upper ? v[k + h] : v[k], upper ? v[k + h + 1] : v[k + 1]);
+			const float2 recv = make_float2(__shfl_xor_sync(0xffffffffu, s0, mask), __shfl_xor_sync(0xffffffffu, s1, mask));
+			const float2 sum = __fadd2_rn(keep, recv);
+			v[k] = sum.x;
+			v[k + 1] = sum.y;
 		}
+	}
+	{
+		const int mask = (N == 16) ? 2 : 1;
+		const bool upper = (lane & mask) != 0;
+		const float send = upper ? v[0] : v[1];
+		const float keep = upper ? v[1] : v[0];
+		v[0] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
 	}
 	if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
@@ -158,6 +169,12 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 
 	// running sum over the splats behind the current one (see the loop body); starts with the background layer
 	float B = T_final * bg_dot_dpixel;
+	// per-pixel upstream gradients in the pairing of the record fields (see the loop body)
+	const float2 g_rg = make_float2(dL_dpixel[0], dL_dpixel[1]);
+	const float2 g_bt = make_float2(dL_dpixel[2], dL_dpixel_t);
+	const float2 g_nxy = make_float2(dL_dpixel_normal[0], dL_dpixel_normal[1]);
+	const float g_nz = dL_dpixel_normal[2];
+	const float2 npix = make_float2(-pxf, -pyf);
 
 	const float ddelx_dx = 0.5 * W;
 	const float ddely_dy = 0.5 * H;
@@ -207,8 +224,9 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 				const int jj = c0 + bpos;
 				const int contributor = pos0 - jj;  // 0-based position in the tile list (backward.cu:837)
 				const uint32_t sa = s_addr + (uint32_t)jj * 16u;
-				const float4 q0 = lds128(sa), q1 = lds128(sa + BATCH * 16u);
-				const float dx = q0.x - pxf, dy = q0.y - pyf;
+				const float4 q0 = lds128(sa), q1 = lds128(sa + BATCH * 16u);  // (mx my A B) (C o ray.x ray.y)
+				const float2 d = __fadd2_rn(make_float2(q0.x, q0.y), npix);   // centre - pixel
+				const float dx = d.x, dy = d.y;
 				const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
 				const float G = expf(power);
 				const float alpha_raw = min(0.99f, q1.y * G);
@@ -225,21 +243,25 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 				// gradients, alpha channel c = 1, background folded in as the last layer) that is exactly
 				//      dL/dalpha = T * S - B / (1 - alpha),       B += alpha T S
 				// -- one running scalar instead of 8 running blends + 8 "last" values (same algebra, different rounding).
+				//
+				// Channels that share a factor are kept in aligned register pairs -- (r,g) (b,t) (nx,ny) on the record side,
+				// (g_r,g_g) (g_b,g_t) (g_nx,g_ny) on the pixel side -- and go through the packed fp32x2 FMUL2 / FFMA2.
 				const float alpha = ok ? alpha_raw : 0.f;
-				const float4 q2 = lds128(sa + 2 * BATCH * 16u);
+				float4 q2 = lds128(sa + 2 * BATCH * 16u);  // r g b t_center
 				float gv[GF];
 				const float inv = __fdividef(1.f, 1.f - alpha);  // shared by T/(1-alpha) and B/(1-alpha)
 				T = T * inv;
 				const float w = alpha * T;  // dchannel_dcolor
-				float S = dL_dalpha;
-				S = fmaf(q2.y, dL_dpixel[0], S);
-				S = fmaf(q2.z, dL_dpixel[1], S);
-				S = fmaf(q2.w, dL_dpixel[2], S);
-				gv[G_COL + 0] = w * dL_dpixel[0];
-				gv[G_COL + 1] = w * dL_dpixel[1];
-				gv[G_COL + 2] = w * dL_dpixel[2];
+				const float2 w2 = make_float2(w, w);
+				if constexpr (DEPTH) q2.w = q2.w + (q1.z * dx + q1.w * dy);  // t = t_center + ray . d
+				float2 S2 = __ffma2_rn(make_float2(q2.x, q2.y), g_rg, make_float2(dL_dalpha, 0.f));
+				S2 = __ffma2_rn(make_float2(q2.z, q2.w), g_bt, S2);
+				const float2 c_rg = __fmul2_rn(w2, g_rg);
+				float2 c_bt = __fmul2_rn(w2, g_bt);  // (dL_dcolor.b, dL_dt before the median term)
+				gv[G_COL + 0] = c_rg.x;
+				gv[G_COL + 1] = c_rg.y;
+				gv[G_COL + 2] = c_bt.x;
 				float dL_dcoords[3] = {0.f, 0.f, 0.f};
-				float dL_dt = 0.f;
 				float4 q3, q4, q5;
 				const bool is_median = ok && contributor == max_contributor - 1;
 				if constexpr (GEO) q3 = lds128(sa + 3 * BATCH * 16u);
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 					const float coord[3] = {q4.x + q4.w * dx + q5.x * dy, q4.y + q5.y * dx + q5.z * dy, q4.z + q5.w * dx + q3.w * dy};
 #pragma unroll
 					for (int ch = 0; ch < 3; ch++) {
-						S = fmaf(coord[ch], dL_dpixel_coord[ch], S);
+						S2.x = fmaf(coord[ch], dL_dpixel_coord[ch], S2.x);
 						dL_dcoords[ch] = w * dL_dpixel_coord[ch];
 						if (is_median) dL_dcoords[ch] += dL_dpixel_mcoord[ch];
 						gv[G_VP + ch] = dL_dcoords[ch];
@@ -259,23 +281,25 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 #pragma unroll
 					for (int k = 25; k < GF; k++) gv[k] = 0.f;
 				}
+				float dL_dt = 0.f;
 				if constexpr (DEPTH) {
-					const float t = q1.z + (q1.w * dx + q2.x * dy);
-					S = fmaf(t, dL_dpixel_t, S);
-					dL_dt = w * dL_dpixel_t;
+					dL_dt = c_bt.y;
 					if (is_median) dL_dt += dL_dpixel_mt;
 				}
 				gv[G_T] = dL_dt;
-				gv[G_RAYX] = dL_dt * dx;
-				gv[G_RAYY] = dL_dt * dy;
+				const float2 g_ray = __fmul2_rn(make_float2(dL_dt, dL_dt), d);
+				gv[G_RAYX] = g_ray.x;
+				gv[G_RAYY] = g_ray.y;
+				float S;
 				if constexpr (GEO) {
-					S = fmaf(q3.x, dL_dpixel_normal[0], S);
-					S = fmaf(q3.y, dL_dpixel_normal[1], S);
-					S = fmaf(q3.z, dL_dpixel_normal[2], S);
-					gv[G_NRM + 0] = w * dL_dpixel_normal[0];
-					gv[G_NRM + 1] = w * dL_dpixel_normal[1];
-					gv[G_NRM + 2] = w * dL_dpixel_normal[2];
+					S2 = __ffma2_rn(make_float2(q3.x, q3.y), g_nxy, S2);
+					const float2 c_n = __fmul2_rn(w2, g_nxy);
+					S = fmaf(q3.z, g_nz, S2.x + S2.y);
+					gv[G_NRM + 0] = c_n.x;
+					gv[G_NRM + 1] = c_n.y;
+					gv[G_NRM + 2] = w * g_nz;
 				} else {
+					S = S2.x + S2.y;
 					gv[G_NRM] = gv[G_NRM + 1] = gv[G_NRM + 2] = 0.f;
 				}
 				const float dL_dopa = T * S - inv * B;
@@ -283,25 +307,24 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 				const float Gm = ok ? G : 0.f;  // the reference skips this pair entirely: every term below carries a factor G
 
 				const float dL_dG = q1.y * dL_dopa;
-				const float gdx = Gm * dx, gdy = Gm * dy;
-				const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
-				const float dG_ddely = -gdy * q1.x - gdx * q0.w;
-				float dL_ddelx = dL_dG * dG_ddelx;
-				float dL_ddely = dL_dG * dG_ddely;
-				gv[G_MABS] = abs(dL_ddelx * ddelx_dx) + abs(dL_ddely * ddely_dy);
+				const float2 gd = __fmul2_rn(make_float2(Gm, Gm), d);  // (G dx, G dy)
+				const float dG_ddelx = -gd.x * q0.z - gd.y * q0.w;
+				const float dG_ddely = -gd.y * q1.x - gd.x * q0.w;
+				float2 dL_ddel = __fmul2_rn(make_float2(dL_dG, dL_dG), make_float2(dG_ddelx, dG_ddely));
+				const float2 ab = __fmul2_rn(dL_ddel, make_float2(ddelx_dx, ddely_dy));
+				gv[G_MABS] = abs(ab.x) + abs(ab.y);
 				if constexpr (COORD) {
-					dL_ddelx += dL_dcoords[0] * q4.w + dL_dcoords[1] * q5.y + dL_dcoords[2] * q5.w;
-					dL_ddely += dL_dcoords[0] * q5.x + dL_dcoords[1] * q5.z + dL_dcoords[2] * q3.w;
+					dL_ddel.x += dL_dcoords[0] * q4.w + dL_dcoords[1] * q5.y + dL_dcoords[2] * q5.w;
+					dL_ddel.y += dL_dcoords[0] * q5.x + dL_dcoords[1] * q5.z + dL_dcoords[2] * q3.w;
 				}
-				if constexpr (DEPTH) {
-					dL_ddelx += dL_dt * q1.w;
-					dL_ddely += dL_dt * q2.x;
-				}
-				gv[G_MX] = dL_ddelx;  // * 0.5 W in backward-preprocess
-				gv[G_MY] = dL_ddely;  // * 0.5 H
-				gv[G_CONX] = -0.5f * gdx * dx * dL_dG;
-				gv[G_CONY] = -0.5f * gdx * dy * dL_dG;
-				gv[G_CONW] = -0.5f * gdy * dy * dL_dG;
+				if constexpr (DEPTH) dL_ddel = __ffma2_rn(make_float2(dL_dt, dL_dt), make_float2(q1.z, q1.w), dL_ddel);
+				gv[G_MX] = dL_ddel.x;  // * 0.5 W in backward-preprocess
+				gv[G_MY] = dL_ddel.y;  // * 0.5 H
+				const float hG = -0.5f * dL_dG;
+				const float2 cxy = __fmul2_rn(__fmul2_rn(make_float2(gd.x, gd.x), d), make_float2(hG, hG));
+				gv[G_CONX] = cxy.x;
+				gv[G_CONY] = cxy.y;
+				gv[G_CONW] = gd.y * dy * hG;
 				gv[G_OPA] = Gm * dL_dopa;
 				warp_reduce_scatter<GF>(gv, lane);
 				float* row = grad_accum + (size_t)lds32(ids_addr + (uint32_t)jj * 4u) * GF;

@@ -47,11 +47,9 @@ __global__ void __launch_bounds__(NTHREADS) render_forward_kernel(
 	bool done = !inside;
 	float T = 1.0f;
 	uint32_t last_contributor = 0, max_contributor = 0xFFFFFFFFu;
-	float C[3] = {0.f, 0.f, 0.f};
-	float weight = 0.f;
+	float2 C01 = {0.f, 0.f}, C2D = {0.f, 0.f}, N01 = {0.f, 0.f}, N2W = {0.f, 0.f};  // (r,g) (b,depth) (nx,ny) (nz,weight)
 	float Coord[3] = {0.f, 0.f, 0.f}, mCoord[3] = {0.f, 0.f, 0.f};
-	float Depth = 0.f, mDepth = 0.f;
-	float Normal[3] = {0.f, 0.f, 0.f};
+	float mDepth = 0.f;
 
 	// ---- pipeline prologue: gather batch 0, prefetch ids of batch 1 ----
 	const size_t rec_stride = (size_t)RFQ * 4;
@@ -110,13 +108,16 @@ __global__ void __launch_bounds__(NTHREADS) render_forward_kernel(
 					continue;
 				}
 				const uint32_t contributor = (uint32_t)(i * BATCH + jj + 1);
-				const float4 q2 = s[2 * BATCH + jj];
+				const float4 q2 = s[2 * BATCH + jj];  // r g b t_center
 				if (ok) {
 					const float aT = alpha * T;
-					C[0] += q2.y * aT;
-					C[1] += q2.z * aT;
-					C[2] += q2.w * aT;
+					const float2 aT2 = make_float2(aT, aT);
+					// (r,g), (b,t), (nx,ny), (nz,1) sit in aligned register pairs: four packed FFMA2 blend 8 channels
+					C01 = __ffma2_rn(make_float2(q2.x, q2.y), aT2, C01);
 					const bool before_median = T > 0.5;
+					float t = 0.f;
+					if constexpr (DEPTH) t = q2.w + (q1.z * dx + q1.w * dy);
+					C2D = __ffma2_rn(make_float2(q2.z, t), aT2, C2D);  // (blue, ray-space depth)
 					if constexpr (GEO) {
 						const float4 q3 = s[3 * BATCH + jj];
 						if constexpr (COORD) {
@@ -131,16 +132,14 @@ __global__ void __launch_bounds__(NTHREADS) render_forward_kernel(
 							if (before_median) { mCoord[0] = cx; mCoord[1] = cy; mCoord[2] = cz; }
 						}
 						if constexpr (DEPTH) {
-							const float t = q1.z + (q1.w * dx + q2.x * dy);
-							Depth += t * aT;
 							if (before_median) mDepth = t;
 						}
-						Normal[0] += q3.x * aT;
-						Normal[1] += q3.y * aT;
-						Normal[2] += q3.z * aT;
+						N01 = __ffma2_rn(make_float2(q3.x, q3.y), aT2, N01);
+						N2W = __ffma2_rn(make_float2(q3.z, 1.f), aT2, N2W);  // (normal z, weight)
 						if (before_median) max_contributor = contributor;
+					} else {
+						N2W.y += aT;
 					}
-					weight += aT;
 					T = test_T;
 					last_contributor = contributor;
 				}
@@ -149,6 +148,9 @@ __global__ void __launch_bounds__(NTHREADS) render_forward_kernel(
 	}
 
 	if (inside) {
+		const float C[3] = {C01.x, C01.y, C2D.x};
+		const float Depth = C2D.y, weight = N2W.y;
+		const float Normal[3] = {N01.x, N01.y, N2W.x};
 		const int pix_id = W * py + px;
 		const size_t HW = (size_t)H * W;
 		n_contrib[pix_id] = last_contributor;

@@ -84,8 +84,8 @@ def ours_views(fwd: dict, sc) -> dict:
     n_contrib = i.take(2 * N, torch.int32, 4).view(2, sc.height, sc.width)
     return dict(totals=totals, records=rec, depths=depths, tiles_touched=tiles_touched, offsets=offsets, clamped=clamped, point_list=point_list,
                 keys=keys, ranges=ranges, n_contrib=n_contrib,
-                means2D=rec[:, 0:2], conic_opacity=torch.stack([rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 5]], 1), ts=rec[:, 6],
-                ray_planes=torch.stack([rec[:, 7], rec[:, 8]], 1), rgb=rec[:, 9:12], normals=rec[:, 12:15],
+                means2D=rec[:, 0:2], conic_opacity=torch.stack([rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 5]], 1), ts=rec[:, 11],
+                ray_planes=rec[:, 6:8], rgb=rec[:, 8:11], normals=rec[:, 12:15],
                 camera_planes=(torch.cat([rec[:, 19:24], rec[:, 15:16]], 1) if coord else None),
                 view_points=(rec[:, 16:19] if coord else None))
 
