@@ -185,6 +185,8 @@ def main():
     multi = world > 1 and a.impl == "ours"
     if multi:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from rade_gs_b200 import multigpu, rawapi, scenes

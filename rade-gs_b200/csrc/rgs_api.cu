@@ -85,11 +85,12 @@ static GeomView carve_geom(char* base, int P, bool coord, size_t scan_bytes, siz
 	return g;
 }
 
-static BinView carve_bin(char* base, size_t R, size_t sort_bytes, size_t* total) {
+static BinView carve_bin(char* base, size_t R, int tiles, size_t sort_bytes, size_t* total) {
 	Carver c(base);
 	BinView b;
 	b.point_list = c.take<uint32_t>(R);
 	b.keys_sorted = c.take<uint64_t>(R);
+	b.hitmask = c.take<uint32_t>(hitmask_words(R, tiles));
 	b.point_list_unsorted = c.take<uint32_t>(R);
 	b.keys_unsorted = c.take<uint64_t>(R);
 	b.sort_temp = c.take<char>(sort_bytes);
@@ -104,6 +105,7 @@ static ImgView carve_img(char* base, int tiles, size_t N, bool coord, bool depth
 	v.ranges = c.take<uint2>(tiles);
 	v.tile_count = c.take<uint32_t>(tiles);
 	v.totals = c.take<uint32_t>(2);
+	v.chunk_base = c.take<uint32_t>(tiles);
 	v.n_contrib = c.take<uint32_t>(2 * N);
 	v.accum_depth = c.take<float>(depth ? N : 0);
 	v.normal_length = c.take<float>((coord || depth) ? N : 0);
@@ -235,10 +237,10 @@ int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_fo
 	const bool tile_path = !force_radix && max_list <= (uint32_t)TILE_SORT_CAP;
 	const size_t sort_bytes = (R > 0 && !tile_path) ? sort_temp_bytes((size_t)R) : 0;
 	size_t bin_bytes = 0;
-	carve_bin(nullptr, (size_t)R, sort_bytes, &bin_bytes);
+	carve_bin(nullptr, (size_t)R, tiles, sort_bytes, &bin_bytes);
 	char* bin_ptr = bufs->binning(bufs->binning_user, bin_bytes);
 	if (!bin_ptr) return fail(RGS_E_ALLOC, "binning buffer callback returned NULL");
-	BinView b = carve_bin(bin_ptr, (size_t)R, sort_bytes, nullptr);
+	BinView b = carve_bin(bin_ptr, (size_t)R, tiles, sort_bytes, nullptr);
 
 	if (P == 0) {
 		RGS_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, (size_t)tiles * sizeof(uint2), s));
@@ -265,7 +267,7 @@ static int backward_views(const rgs_camera* cam, const rgs_gaussians* gs, const 
 	const size_t scan_bytes = p.P > 0 ? scan_temp_bytes(p.P) : 0;
 	g = carve_geom(const_cast<char*>(in->geom_buffer), p.P, p.coord, scan_bytes, nullptr);
 	const size_t sort_bytes = in->num_rendered > 0 ? sort_temp_bytes((size_t)in->num_rendered) : 0;
-	b = carve_bin(const_cast<char*>(in->binning_buffer), (size_t)in->num_rendered, sort_bytes, nullptr);
+	b = carve_bin(const_cast<char*>(in->binning_buffer), (size_t)in->num_rendered, p.grid_x * p.grid_y, sort_bytes, nullptr);
 	img = carve_img(const_cast<char*>(in->image_buffer), p.grid_x * p.grid_y, N, p.coord, p.depth, nullptr);
 	return RGS_OK;
 }
@@ -334,7 +336,7 @@ int32_t rgs_debug_get_views(const rgs_camera* cam, int32_t P, int64_t num_render
 	const size_t scan_bytes = P > 0 ? scan_temp_bytes(P) : 0;
 	GeomView g = carve_geom(const_cast<char*>(geom_buffer), P, coord, scan_bytes, nullptr);
 	const size_t sort_bytes = num_rendered > 0 ? sort_temp_bytes((size_t)num_rendered) : 0;
-	BinView b = carve_bin(const_cast<char*>(binning_buffer), (size_t)num_rendered, sort_bytes, nullptr);
+	BinView b = carve_bin(const_cast<char*>(binning_buffer), (size_t)num_rendered, grid_x * grid_y, sort_bytes, nullptr);
 	ImgView img = carve_img(const_cast<char*>(image_buffer), grid_x * grid_y, N, coord, depth, nullptr);
 	views->point_list = b.point_list;
 	views->point_list_keys = b.keys_sorted;

@@ -122,40 +122,47 @@ void launch_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, cons
 // =====================================================================================================================
 
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
-                                                          uint32_t* __restrict__ totals) {
-	__shared__ uint32_t s_warp[32];
-	__shared__ uint32_t s_carry, s_max;
+                                                          uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ totals) {
+	__shared__ uint32_t s_warp[32], s_warp2[32];
+	__shared__ uint32_t s_carry, s_carry2, s_max;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) { s_carry = 0; s_max = 0; }
+	if (tid == 0) { s_carry = 0; s_carry2 = 0; s_max = 0; }
 	__syncthreads();
 	uint32_t local_max = 0;
 	for (int base = 0; base < tiles; base += 1024) {
 		const int t = base + tid;
 		const uint32_t c = t < tiles ? tile_count[t] : 0u;
 		local_max = max(local_max, c);
-		uint32_t v = c;  // inclusive warp scan
+		const uint32_t ch = (c + 31u) >> 5;  // 32-instance chunks of this tile (hit-mask words per pixel block)
+		uint32_t v = c, v2 = ch;  // inclusive warp scans
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
 			const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
-			if (lane >= o) v += n;
+			const uint32_t n2 = __shfl_up_sync(0xffffffffu, v2, o);
+			if (lane >= o) { v += n; v2 += n2; }
 		}
-		if (lane == 31) s_warp[warp] = v;
+		if (lane == 31) { s_warp[warp] = v; s_warp2[warp] = v2; }
 		__syncthreads();
 		if (warp == 0) {
-			uint32_t w = s_warp[lane];
+			uint32_t w = s_warp[lane], w2 = s_warp2[lane];
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {
 				const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
-				if (lane >= o) w += n;
+				const uint32_t n2 = __shfl_up_sync(0xffffffffu, w2, o);
+				if (lane >= o) { w += n; w2 += n2; }
 			}
 			s_warp[lane] = w;
+			s_warp2[lane] = w2;
 		}
 		__syncthreads();
-		const uint32_t carry = s_carry;
-		const uint32_t incl = carry + v + (warp > 0 ? s_warp[warp - 1] : 0u);
-		if (t < tiles) ranges[t] = c ? make_uint2(incl - c, incl) : make_uint2(0u, 0u);  // empty tiles stay (0,0) like the reference's memset
+		const uint32_t incl = s_carry + v + (warp > 0 ? s_warp[warp - 1] : 0u);
+		const uint32_t incl2 = s_carry2 + v2 + (warp > 0 ? s_warp2[warp - 1] : 0u);
+		if (t < tiles) {
+			ranges[t] = c ? make_uint2(incl - c, incl) : make_uint2(0u, 0u);  // empty tiles stay (0,0) like the reference's memset
+			chunk_base[t] = incl2 - ch;
+		}
 		__syncthreads();
-		if (tid == 1023) s_carry = incl;
+		if (tid == 1023) { s_carry = incl; s_carry2 = incl2; }
 		__syncthreads();
 	}
 #pragma unroll
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, const uint32
 }
 
 void launch_tile_scan(const FwdParams& p, ImgView img, cudaStream_t s) {
-	tile_scan_kernel<<<1, 1024, 0, s>>>(p.grid_x * p.grid_y, img.tile_count, img.ranges, img.totals);
+	tile_scan_kernel<<<1, 1024, 0, s>>>(p.grid_x * p.grid_y, img.tile_count, img.ranges, img.chunk_base, img.totals);
 	count_launch();
 }
 

@@ -69,6 +69,8 @@ struct GeomView {
 struct BinView {
 	uint32_t* point_list;          // [R] sorted Gaussian ids
 	uint64_t* keys_sorted;         // [R]
+	uint32_t* hitmask;             // [(R/32 + tiles + 1) * 8] per 32-instance chunk: one ballot word per 8x4 pixel block of the tile,
+	                               // written by forward-render (which splats can reach alpha >= 1/255 in the block), read by backward
 	uint32_t* point_list_unsorted; // [R]
 	uint64_t* keys_unsorted;       // [R]
 	char* sort_temp;
@@ -79,6 +81,7 @@ struct ImgView {
 	uint2* ranges;        // [tiles]
 	uint32_t* tile_count; // [tiles] instances per tile (tile-bucket binning); counted down to 0 by the scatter
 	uint32_t* totals;     // [2]     num_rendered, longest tile list
+	uint32_t* chunk_base; // [tiles] first 32-instance chunk of each tile in BinView::hitmask (exclusive scan of ceil(n/32))
 	uint32_t* n_contrib;  // [2 * N]
 	float* accum_depth;   // [N]
 	float* normal_length; // [N]
@@ -208,6 +211,7 @@ struct RenderOut {
 	float *color, *coord, *mcoord, *alpha, *normal, *depth, *mdepth;
 };
 void launch_render_forward(const FwdParams& p, GeomView g, BinView b, ImgView img, RenderOut out, cudaStream_t s);
+__host__ __device__ inline size_t hitmask_words(size_t R, int tiles) { return (R / 32 + (size_t)tiles + 1) * 8; }
 
 struct RenderGradIn {
 	const float *d_color, *d_coord, *d_mcoord, *d_depth, *d_mdepth, *d_alpha, *d_normal;

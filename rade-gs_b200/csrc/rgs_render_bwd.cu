@@ -12,7 +12,7 @@
 //     in backward-preprocess;
 //   * the tile list is cut at the block-wide maximum of last_contributor (nothing behind it can receive
 //     gradient, backward.cu:838-839), each warp additionally skips splats behind ITS maximum and splats
-//     that cannot reach alpha >= 1/255 inside its 8x4 pixel block (same conservative test as forward);
+//     that cannot reach alpha >= 1/255 inside its 8x4 pixel block -- read from the ballots forward-render stored;
 //   * records are gathered with cp.async into a 2-stage ring, like forward, but walking the list from
 //     the back.
 #include "rgs_render_common.cuh"
@@ -50,6 +50,11 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane) {
 	if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
 __device__ __forceinline__ int lds32(uint32_t addr) {
 	int v;
 	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -71,7 +76,8 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
     const float* __restrict__ accum_depth, const float* __restrict__ accum_coord, const float* __restrict__ normal_length,
     const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_coords, const float* __restrict__ dL_dpixel_mcoords,
     const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dpixel_mdepths, const float* __restrict__ dL_dalphas,
-    const float* __restrict__ dL_dpixel_normals, float* __restrict__ grad_accum) {
+    const float* __restrict__ dL_dpixel_normals, float* __restrict__ grad_accum, const uint32_t* __restrict__ chunk_base,
+    const uint32_t* __restrict__ hitmask) {
 	constexpr bool GEO = COORD || DEPTH;
 	constexpr int RFQ = COORD ? 6 : 4;
 	constexpr int GF = COORD ? GRAD_FLOATS_COORD : GRAD_FLOATS_BASE;
@@ -92,6 +98,7 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 	const size_t HW = (size_t)H * W;
 
 	const uint2 range = ranges[tile_y * grid_x + tile_x];
+	const uint32_t* my_mask = hitmask + (size_t)chunk_base[tile_y * grid_x + tile_x] * 8 + warp;
 
 	// ---- per-pixel state from forward (backward.cu:704-781) ----
 	const float T_final = inside ? (1 - alphas[pix_id]) : 0;
@@ -210,14 +217,23 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 		const int pos0 = n - 1 - i * BATCH;  // list position of staged index 0
 		if (pos0 - (cnt - 1) >= warp_last) continue;  // whole batch is behind this warp's last contributor
 
+		// hit masks of forward-render for the positions of this batch: word k covers list positions [32k, 32k+32);
+		// lane l fetches word (pos0>>5) - l, chunks below pick theirs up with a shuffle
+		const int k_hi = pos0 >> 5;
+		uint32_t wl = 0;
+		if (lane <= 9 && k_hi - lane >= 0) wl = __ldg(my_mask + (size_t)(k_hi - lane) * 8);
+
 		for (int c0 = 0; c0 < cnt; c0 += 32) {
-			const int j = c0 + lane;
-			bool hit = false;
-			if (j < cnt && (pos0 - j) < warp_last) {
-				const float4 a = s[j], b = s[BATCH + j];
-				hit = splat_hits_box(a.x, a.y, a.z, a.w, b.x, b.y, wx0, wx1, wy0, wy1);
-			}
-			unsigned m = __ballot_sync(0xffffffffu, hit);
+			// staged index j of this chunk <-> list position hi - j
+			const int hi = pos0 - c0, lo_pos = hi - 31;
+			const int k0 = lo_pos >> 5;  // floor, -1 when the chunk reaches below position 0
+			const uint32_t w0 = __shfl_sync(0xffffffffu, wl, (k_hi - k0) & 31);
+			const uint32_t w1 = __shfl_sync(0xffffffffu, wl, (k_hi - k0 - 1) & 31);
+			unsigned m = __brev(__funnelshift_r(w0, w1, lo_pos & 31));  // bit j <-> position hi - j
+			const int valid = min(32, cnt - c0);                       // staged entries in this chunk
+			if (valid < 32) m &= (1u << valid) - 1u;
+			const int behind = hi - warp_last + 1;                      // entries j < behind sit at or behind warp_last
+			if (behind > 0) m = behind >= 32 ? 0u : (m & ~((1u << behind) - 1u));
 			while (m) {
 				const int bpos = __ffs(m) - 1;
 				m &= m - 1;
@@ -249,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 				const float alpha = ok ? alpha_raw : 0.f;
 				float4 q2 = lds128(sa + 2 * BATCH * 16u);  // r g b t_center
 				float gv[GF];
-				const float inv = __fdividef(1.f, 1.f - alpha);  // shared by T/(1-alpha) and B/(1-alpha)
+				const float inv = rcp_approx(1.f - alpha);  // 1 - alpha in [0.01, 1]: bare MUFU.RCP; shared by T/(1-alpha) and B/(1-alpha)
 				T = T * inv;
 				const float w = alpha * T;  // dchannel_dcolor
 				const float2 w2 = make_float2(w, w);
@@ -351,7 +367,7 @@ static void launch_variant(const FwdParams& p, GeomView g, BinView b, ImgView im
 	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
 	kern<<<grid, NTHREADS, smem, s>>>(img.ranges, b.point_list, g.records, p.W, p.H, p.grid_x, p.row_begin, p.focal_x, p.focal_y, p.background,
 	                                 gin.out_alpha, gin.out_normal, img.n_contrib, img.accum_depth, img.accum_coord, img.normal_length,
-	                                 gin.d_color, gin.d_coord, gin.d_mcoord, gin.d_depth, gin.d_mdepth, gin.d_alpha, gin.d_normal, grad_accum);
+	                                 gin.d_color, gin.d_coord, gin.d_mcoord, gin.d_depth, gin.d_mdepth, gin.d_alpha, gin.d_normal, grad_accum, img.chunk_base, b.hitmask);
 	count_launch();
 }
 

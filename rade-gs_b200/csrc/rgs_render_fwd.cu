@@ -11,6 +11,8 @@
 //     conservative minimum of the conic form over the block -- a splat whose best pixel cannot reach
 //     alpha >= 1/255 is skipped for the whole warp (result-identical: the reference would `continue`
 //     on every one of those pixels, forward.cu:566-567) -- and only the survivors (ballot) are blended;
+//   * the ballots are also stored (one word per pixel block per 32 instances): backward-render reuses them instead of
+//     repeating the test;
 //   * warp-ballot early-out when all 32 pixels are saturated, block-wide exit as in the reference;
 //   * every output plane is written by the kernel (zeros for the planes of a disabled variant), so the
 //     host side allocates with empty() instead of seven fill kernels (rasterize_points.cu:71-78).
@@ -19,12 +21,13 @@
 namespace rgs {
 
 template <bool COORD, bool DEPTH>
-__global__ void __launch_bounds__(NTHREADS) render_forward_kernel(
+__global__ void __launch_bounds__(NTHREADS, (COORD ? 4 : 5)) render_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float* __restrict__ records,
     int W, int H, int grid_x, int row_begin, float focal_x, float focal_y, const float* __restrict__ bg_color,
     float* __restrict__ out_color, float* __restrict__ out_coord, float* __restrict__ out_mcoord, float* __restrict__ out_alpha,
     float* __restrict__ out_normal, float* __restrict__ out_depth, float* __restrict__ out_mdepth,
-    uint32_t* __restrict__ n_contrib, float* __restrict__ accum_depth, float* __restrict__ accum_coord, float* __restrict__ normal_length) {
+    uint32_t* __restrict__ n_contrib, float* __restrict__ accum_depth, float* __restrict__ accum_coord, float* __restrict__ normal_length,
+    const uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ hitmask) {
 	constexpr bool GEO = COORD || DEPTH;
 	constexpr int RFQ = COORD ? 6 : 4;  // float4 chunks per record
 	extern __shared__ float4 smem[];    // [2][RFQ][BATCH]
@@ -42,6 +45,8 @@ __global__ void __launch_bounds__(NTHREADS) render_forward_kernel(
 
 	const uint2 range = ranges[tile_y * grid_x + tile_x];
 	const int n = (int)(range.y - range.x);
+	// this warp's column of the tile's hit-mask block: one ballot word per 32 instances, kept for backward-render
+	uint32_t* my_mask = hitmask + (size_t)chunk_base[tile_y * grid_x + tile_x] * 8 + warp;
 	const int rounds = (n + BATCH - 1) / BATCH;
 
 	bool done = !inside;
@@ -80,6 +85,7 @@ __global__ void __launch_bounds__(NTHREADS) render_forward_kernel(
 
 		if (!warp_has_pixels || __all_sync(0xffffffffu, done)) continue;
 
+		unsigned batch_mask = 0;
 		for (int c0 = 0; c0 < cnt; c0 += 32) {
 			const int j = c0 + lane;
 			bool hit = false;
@@ -88,6 +94,7 @@ __global__ void __launch_bounds__(NTHREADS) render_forward_kernel(
 				hit = splat_hits_box(a.x, a.y, a.z, a.w, b.x, b.y, wx0, wx1, wy0, wy1);
 			}
 			unsigned m = __ballot_sync(0xffffffffu, hit);
+			if (lane == (c0 >> 5)) batch_mask = m;  // lane c keeps the ballot of chunk c; stored once per batch below
 			while (m) {
 				const int bpos = __ffs(m) - 1;
 				m &= m - 1;
@@ -145,6 +152,7 @@ __global__ void __launch_bounds__(NTHREADS) render_forward_kernel(
 				}
 			}
 		}
+		if (lane < ((cnt + 31) >> 5)) my_mask[(size_t)(i * (BATCH / 32) + lane) * 8] = batch_mask;  // only this tile's chunks; untested ones read as 0
 	}
 
 	if (inside) {
@@ -215,7 +223,7 @@ static void launch_variant(const FwdParams& p, GeomView g, BinView b, ImgView im
 	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
 	kern<<<grid, NTHREADS, smem, s>>>(img.ranges, b.point_list, g.records, p.W, p.H, p.grid_x, p.row_begin, p.focal_x, p.focal_y, p.background,
 	                                 out.color, out.coord, out.mcoord, out.alpha, out.normal, out.depth, out.mdepth, img.n_contrib,
-	                                 img.accum_depth, img.accum_coord, img.normal_length);
+	                                 img.accum_depth, img.accum_coord, img.normal_length, img.chunk_base, b.hitmask);
 	count_launch();
 }
 

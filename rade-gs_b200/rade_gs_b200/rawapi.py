@@ -81,6 +81,7 @@ def ours_views(fwd: dict, sc) -> dict:
     ranges = i.take(tiles * 2, torch.int32, 4).view(tiles, 2)
     i.take(tiles, torch.int32, 4)   # tile_count (counted back down to zero by the scatter)
     totals = i.take(2, torch.int32, 4)
+    i.take(tiles, torch.int32, 4)   # chunk_base
     n_contrib = i.take(2 * N, torch.int32, 4).view(2, sc.height, sc.width)
     return dict(totals=totals, records=rec, depths=depths, tiles_touched=tiles_touched, offsets=offsets, clamped=clamped, point_list=point_list,
                 keys=keys, ranges=ranges, n_contrib=n_contrib,
