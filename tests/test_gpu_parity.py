@@ -239,3 +239,62 @@ def test_c2_slabs_compose_to_the_whole(c2):
         # float-atomic summation order differs between the two paths; at 1M splats a handful of ill-conditioned splats
         # amplify that to ~2e-3 of the tensor maximum (the reference's own run-to-run spread is 1.6e-3 here)
         grad_close_gpu(o.cpu().numpy(), whole[k].cpu().numpy(), k, rel=1e-3, elem=1e-2)
+
+
+def _oracle_inputs(sc, coord, depth, ks, deg, shs=None):
+    import oracle
+    return oracle.Inputs(sc.means3D.numpy(), sc.opacities.numpy(), sc.viewmatrix.numpy(), sc.projmatrix.numpy(), sc.campos.numpy(), sc.bg.numpy(),
+                         sc.width, sc.height, sc.tanfovx, sc.tanfovy, shs=(sc.shs if shs is None else shs).numpy(), scales=sc.scales.numpy(),
+                         rotations=sc.rotations.numpy(), sh_degree=deg, kernel_size=ks, require_coord=coord, require_depth=depth)
+
+
+def test_long_tile_list_takes_the_radix_path():
+    """A tile list longer than the shared-memory sort capacity (8192) must fall back to the global radix path and
+    still give the reference order: 12k splats piled onto a few pixels."""
+    import oracle
+    from rade_gs_b200 import rawapi, scenes
+    sc = scenes.make_scene(12000, 64, 48, 200.0, -4.0, seed=31)
+    sc.means3D[:, 0] = 0.02 * torch.randn(12000, generator=torch.Generator().manual_seed(1))
+    sc.means3D[:, 1] = 0.02 * torch.randn(12000, generator=torch.Generator().manual_seed(2))
+    sc.opacities[:] = 0.02  # keep transmittance alive so the whole list matters
+    grads = scenes.make_upstream_grads(sc.height, sc.width, seed=32)
+    fo = oracle.forward(_oracle_inputs(sc, False, True, 0.0, 3))
+    scd = sc.to(DEV)
+    f = rawapi.forward(_C(), scd, False, True)
+    v = rawapi.ours_views(f, scd)
+    assert int(v["totals"][1]) > 8192, "scene did not produce a long tile list"
+    assert f["num_rendered"] == fo["num_rendered"]
+    assert np.array_equal(v["point_list"].cpu().numpy().astype(np.uint32), fo["binning"]["point_list"])
+    assert np.array_equal(v["ranges"].cpu().numpy().astype(np.uint32), fo["binning"]["ranges"])
+    for k in ("color", "alpha", "depth", "normal"):
+        image_close(f[k].cpu().numpy(), fo[k], IMG_OUTLIER_FRAC_CPU, k)
+    b = rawapi.backward(_C(), scd, f, {k: v_.to(DEV) for k, v_ in grads.items()})
+    bo = oracle.backward(_oracle_inputs(sc, False, True, 0.0, 3), fo, {k: v_.numpy() for k, v_ in grads.items()})
+    for k in ("means3D", "sh", "opacity", "scales"):
+        grad_close_cpu(b[k].cpu().numpy(), bo[k], k)
+
+
+@pytest.mark.parametrize("M,deg,W,H", [(1, 0, 70, 50), (4, 1, 33, 17), (9, 2, 96, 64)])
+def test_sh_storage_sizes_and_ragged_images(M, deg, W, H):
+    """SH tensors with fewer stored coefficients ([P,1,3], [P,4,3], [P,9,3]: rows of 12/48/108 bytes, the last two not
+    16-byte multiples of the row index) and image sizes that are not multiples of the 16x16 tile."""
+    import oracle
+    from rade_gs_b200 import rawapi, scenes
+    sc = scenes.make_scene(2500, W, H, 0.9 * W, -2.4, seed=40 + M, view=scenes.look_at_view((0.2, 0.1, -0.3), (0.0, 0.0, 6.0)), bg=(0.05, 0.1, 0.2))
+    shs = sc.shs[:, :M].contiguous()
+    grads = scenes.make_upstream_grads(H, W, seed=50 + M)
+    inp = _oracle_inputs(sc, True, True, 0.1, deg, shs=shs)
+    fo = oracle.forward(inp)
+    bo = oracle.backward(inp, fo, {k: v.numpy() for k, v in grads.items()})
+    scd = sc.to(DEV)
+    scd.shs = shs.to(DEV)
+    f = rawapi.forward(_C(), scd, True, True, kernel_size=0.1, sh_degree=deg)
+    b = rawapi.backward(_C(), scd, f, {k: v.to(DEV) for k, v in grads.items()})
+    v = rawapi.ours_views(f, scd)
+    assert f["num_rendered"] == fo["num_rendered"] and np.array_equal(f["radii"].cpu().numpy(), fo["radii"])
+    assert np.array_equal(v["point_list"].cpu().numpy().astype(np.uint32), fo["binning"]["point_list"])
+    assert b["sh"].shape == (2500, M, 3)
+    for k in IMG_KEYS:
+        image_close(f[k].cpu().numpy(), fo[k], IMG_OUTLIER_FRAC_CPU, k)
+    for k in GRAD_KEYS:
+        grad_close_cpu(b[k].cpu().numpy(), bo[k], k)
