@@ -156,6 +156,20 @@ int32_t rgs_backward(const rgs_camera* cam, const rgs_gaussians* g, const rgs_ba
 int32_t rgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                          uint8_t* present, void* cuda_stream);
 
+/* ---- next row of the path, opt-in: the per-Gaussian arithmetic directly around the rasterizer call ----
+ * rgs_activate_*: fused GaussianModel.get_scaling_n_opacity_with_3D_filter + get_rotation (reference
+ * scene/gaussian_model.py:156-166, 125-126): raw parameters -> (scales [P,3], opacity [P], unit rotations [P,4]) and back.
+ * rgs_densification_stats: train.py:187-188 + GaussianModel.add_densification_stats (scene/gaussian_model.py:743-747) in one
+ * pass over the Gaussians with radii > 0; max_radii2D may be NULL. */
+int32_t rgs_activate_forward(int32_t P, const float* raw_scaling, const float* raw_opacity, const float* raw_rotation,
+                             const float* filter_3D, float* scales, float* opacity, float* rotations, void* cuda_stream);
+int32_t rgs_activate_backward(int32_t P, const float* raw_scaling, const float* raw_opacity, const float* raw_rotation,
+                              const float* filter_3D, const float* g_scales, const float* g_opacity, const float* g_rotations,
+                              float* d_raw_scaling, float* d_raw_opacity, float* d_raw_rotation, void* cuda_stream);
+int32_t rgs_densification_stats(int32_t P, const float* means2D_grad, const int32_t* radii, float* grad_accum,
+                                float* grad_accum_abs, float* grad_accum_abs_max, float* denom, float* max_radii2D,
+                                void* cuda_stream);
+
 /* Introspection for parity tests: views into the private buffers written by rgs_forward
  * (the reference keeps the same data at BinningState::point_list / ImageState::ranges,
  * rasterizer_impl.cu:237-250,224-235).  Pointers are device addresses inside the given buffers. */

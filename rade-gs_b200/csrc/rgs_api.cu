@@ -327,6 +327,40 @@ int32_t rgs_mark_visible(int32_t P, const float* means3D, const float* viewmatri
 	return RGS_OK;
 }
 
+int32_t rgs_activate_forward(int32_t P, const float* raw_scaling, const float* raw_opacity, const float* raw_rotation, const float* filter_3D,
+                             float* scales, float* opacity, float* rotations, void* cuda_stream) {
+	if (P < 0) return fail(RGS_E_INVALID, "negative Gaussian count");
+	if (P == 0) return RGS_OK;
+	if (!raw_scaling || !raw_opacity || !raw_rotation || !filter_3D || !scales || !opacity || !rotations) return fail(RGS_E_INVALID, "null pointer");
+	launch_activate_forward(P, raw_scaling, raw_opacity, raw_rotation, filter_3D, scales, opacity, rotations, (cudaStream_t)cuda_stream);
+	cudaError_t e = cudaGetLastError();
+	return e == cudaSuccess ? (int32_t)RGS_OK : fail(RGS_E_CUDA, cudaGetErrorString(e));
+}
+
+int32_t rgs_activate_backward(int32_t P, const float* raw_scaling, const float* raw_opacity, const float* raw_rotation, const float* filter_3D,
+                              const float* g_scales, const float* g_opacity, const float* g_rotations, float* d_raw_scaling, float* d_raw_opacity,
+                              float* d_raw_rotation, void* cuda_stream) {
+	if (P < 0) return fail(RGS_E_INVALID, "negative Gaussian count");
+	if (P == 0) return RGS_OK;
+	if (!raw_scaling || !raw_opacity || !raw_rotation || !filter_3D || !g_scales || !g_opacity || !g_rotations || !d_raw_scaling || !d_raw_opacity ||
+	    !d_raw_rotation)
+		return fail(RGS_E_INVALID, "null pointer");
+	launch_activate_backward(P, raw_scaling, raw_opacity, raw_rotation, filter_3D, g_scales, g_opacity, g_rotations, d_raw_scaling, d_raw_opacity,
+	                         d_raw_rotation, (cudaStream_t)cuda_stream);
+	cudaError_t e = cudaGetLastError();
+	return e == cudaSuccess ? (int32_t)RGS_OK : fail(RGS_E_CUDA, cudaGetErrorString(e));
+}
+
+int32_t rgs_densification_stats(int32_t P, const float* means2D_grad, const int32_t* radii, float* grad_accum, float* grad_accum_abs,
+                                float* grad_accum_abs_max, float* denom, float* max_radii2D, void* cuda_stream) {
+	if (P < 0) return fail(RGS_E_INVALID, "negative Gaussian count");
+	if (P == 0) return RGS_OK;
+	if (!means2D_grad || !radii || !grad_accum || !grad_accum_abs || !grad_accum_abs_max || !denom) return fail(RGS_E_INVALID, "null pointer");
+	launch_densification_stats(P, means2D_grad, radii, grad_accum, grad_accum_abs, grad_accum_abs_max, denom, max_radii2D, (cudaStream_t)cuda_stream);
+	cudaError_t e = cudaGetLastError();
+	return e == cudaSuccess ? (int32_t)RGS_OK : fail(RGS_E_CUDA, cudaGetErrorString(e));
+}
+
 int32_t rgs_debug_get_views(const rgs_camera* cam, int32_t P, int64_t num_rendered, const char* geom_buffer, const char* binning_buffer,
                             const char* image_buffer, rgs_debug_views* views) {
 	if (!cam || !views) return fail(RGS_E_INVALID, "null pointer");

@@ -335,12 +335,8 @@ void launch_tile_binning(const FwdParams& p, GeomView g, BinView b, ImgView img,
 	                                                  p.row_begin, p.row_end, img.ranges, img.tile_count, b.keys_unsorted);
 	const int cap = (max((int)max_list, 256) + 255) & ~255;  // keys per ping-pong buffer
 	const size_t smem = (size_t)2 * (cap + (cap >> 4)) * sizeof(uint64_t);
-	static size_t configured = 0;
-	if (smem > 48 * 1024 && smem > configured) {
-		const size_t most = (size_t)2 * (TILE_SORT_CAP + (TILE_SORT_CAP >> 4)) * sizeof(uint64_t);
-		cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
-		configured = most;
-	}
+	static size_t configured[64] = {};
+	if (smem > 48 * 1024) ensure_dynamic_smem(tile_sort_kernel, (size_t)2 * (TILE_SORT_CAP + (TILE_SORT_CAP >> 4)) * sizeof(uint64_t), configured);
 	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
 	tile_sort_kernel<<<grid, SORT_THREADS, smem, s>>>(img.ranges, p.grid_x, p.row_begin, b.keys_unsorted, b.point_list, b.keys_sorted, cap);
 	count_launch(2);

@@ -183,6 +183,19 @@ __device__ constexpr float kSH3[7] = {-0.5900435899266435f, 2.890611442640554f, 
 // ---- host-side launch bookkeeping -----------------------------------------------------------------
 void count_launch(int n = 1);
 
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (the attribute is per device and per
+// function; remembered per device so the driver call happens once, also when one process drives several GPUs).
+template <typename Kernel>
+inline void ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&configured)[64]) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	dev &= 63;
+	if (bytes > configured[dev]) {
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+		configured[dev] = bytes;
+	}
+}
+
 // kernels' host launchers (one translation unit each)
 struct FwdParams {
 	int P, D, M, W, H;
@@ -223,5 +236,14 @@ struct ParamGradOut {
 	float *d_means2D, *d_colors, *d_opacity, *d_means3D, *d_cov3D, *d_sh, *d_scales, *d_rotations;
 };
 void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s);
+
+// fused activations / densification statistics (rgs_activation.cu)
+void launch_activate_forward(int P, const float* raw_scaling, const float* raw_opacity, const float* raw_rotation, const float* filter_3D, float* scales,
+                             float* opacity, float* rotations, cudaStream_t s);
+void launch_activate_backward(int P, const float* raw_scaling, const float* raw_opacity, const float* raw_rotation, const float* filter_3D,
+                              const float* g_scales, const float* g_opacity, const float* g_rotations, float* d_raw_scaling, float* d_raw_opacity,
+                              float* d_raw_rotation, cudaStream_t s);
+void launch_densification_stats(int P, const float* means2D_grad, const int* radii, float* grad_accum, float* grad_accum_abs, float* grad_accum_abs_max,
+                                float* denom, float* max_radii2D, cudaStream_t s);
 
 }  // namespace rgs

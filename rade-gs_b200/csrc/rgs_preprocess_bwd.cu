@@ -491,11 +491,8 @@ void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii
 	if (p.shs != nullptr && out.d_sh != nullptr && p.M > 0) {
 		const int stride = (3 * p.M) | 1;
 		const size_t smem = (size_t)SH_WARPS * 32 * stride * sizeof(float);
-		static size_t configured = 0;
-		if (smem > 48 * 1024 && smem > configured) {
-			cudaFuncSetAttribute(sh_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			configured = smem;
-		}
+		static size_t configured[64] = {};
+		if (smem > 48 * 1024) ensure_dynamic_smem(sh_backward_kernel, smem, configured);
 		const int per_block = SH_WARPS * 32;
 		sh_backward_kernel<<<(p.P + per_block - 1) / per_block, per_block, smem, s>>>(p.P, p.D, p.M, p.means3D, p.cam_pos, p.shs, radii, g.clamped,
 		                                                                               grad_accum, grad_floats(p.coord), out.d_sh, out.d_means3D);

@@ -359,11 +359,8 @@ static void launch_variant(const FwdParams& p, GeomView g, BinView b, ImgView im
 	constexpr int RFQ = COORD ? 6 : 4;
 	const size_t smem = (size_t)2 * RFQ * BATCH * sizeof(float4) + (size_t)2 * BATCH * sizeof(int);
 	auto kern = render_backward_kernel<COORD, DEPTH>;
-	static bool configured = false;
-	if (!configured) {
-		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		configured = true;
-	}
+	static size_t configured[64] = {};
+	ensure_dynamic_smem(kern, smem, configured);
 	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
 	kern<<<grid, NTHREADS, smem, s>>>(img.ranges, b.point_list, g.records, p.W, p.H, p.grid_x, p.row_begin, p.focal_x, p.focal_y, p.background,
 	                                 gin.out_alpha, gin.out_normal, img.n_contrib, img.accum_depth, img.accum_coord, img.normal_length,

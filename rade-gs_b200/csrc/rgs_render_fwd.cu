@@ -215,11 +215,8 @@ static void launch_variant(const FwdParams& p, GeomView g, BinView b, ImgView im
 	constexpr int RFQ = COORD ? 6 : 4;
 	const size_t smem = (size_t)2 * RFQ * BATCH * sizeof(float4);
 	auto kern = render_forward_kernel<COORD, DEPTH>;
-	static bool configured = false;
-	if (!configured) {
-		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		configured = true;
-	}
+	static size_t configured[64] = {};
+	ensure_dynamic_smem(kern, smem, configured);
 	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
 	kern<<<grid, NTHREADS, smem, s>>>(img.ranges, b.point_list, g.records, p.W, p.H, p.grid_x, p.row_begin, p.focal_x, p.focal_y, p.background,
 	                                 out.color, out.coord, out.mcoord, out.alpha, out.normal, out.depth, out.mdepth, img.n_contrib,

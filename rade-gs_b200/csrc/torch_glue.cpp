@@ -367,6 +367,59 @@ BwdResult BackwardPreprocessCUDA(const torch::Tensor& grad_accum, const torch::T
 	return std::make_tuple(gt.means2D, gt.colors, gt.opacity, gt.means3D, gt.cov3D, gt.sh, gt.scales, gt.rotations);
 }
 
+// ---- fused activations / densification statistics (opt-in) --------------------------------------------
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> ActivateForward(const torch::Tensor& raw_scaling, const torch::Tensor& raw_opacity,
+                                                                        const torch::Tensor& raw_rotation, const torch::Tensor& filter_3D) {
+	TORCH_CHECK(raw_scaling.is_cuda(), "raw_scaling must be a CUDA tensor: no CPU path");
+	const c10::cuda::CUDAGuard guard(raw_scaling.device());
+	const int P = raw_scaling.size(0);
+	torch::Tensor s = as_input(raw_scaling, raw_scaling, "raw_scaling"), o = as_input(raw_opacity, raw_scaling, "raw_opacity"),
+	              r = as_input(raw_rotation, raw_scaling, "raw_rotation"), f = as_input(filter_3D, raw_scaling, "filter_3D");
+	TORCH_CHECK(s.numel() == 3 * (int64_t)P && o.numel() == P && r.numel() == 4 * (int64_t)P && f.numel() == P, "activate: shapes must be [P,3] [P,1] [P,4] [P,1]");
+	torch::Tensor scales = torch::empty({P, 3}, s.options()), opacity = torch::empty({P, 1}, s.options()), rot = torch::empty({P, 4}, s.options());
+	if (P)
+		check(rgs_activate_forward(P, s.data_ptr<float>(), o.data_ptr<float>(), r.data_ptr<float>(), f.data_ptr<float>(), scales.data_ptr<float>(),
+		                           opacity.data_ptr<float>(), rot.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
+	return std::make_tuple(scales, opacity, rot);
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> ActivateBackward(const torch::Tensor& raw_scaling, const torch::Tensor& raw_opacity,
+                                                                         const torch::Tensor& raw_rotation, const torch::Tensor& filter_3D,
+                                                                         const torch::Tensor& g_scales, const torch::Tensor& g_opacity,
+                                                                         const torch::Tensor& g_rotations) {
+	const c10::cuda::CUDAGuard guard(raw_scaling.device());
+	const int P = raw_scaling.size(0);
+	torch::Tensor s = as_input(raw_scaling, raw_scaling, "raw_scaling"), o = as_input(raw_opacity, raw_scaling, "raw_opacity"),
+	              r = as_input(raw_rotation, raw_scaling, "raw_rotation"), f = as_input(filter_3D, raw_scaling, "filter_3D"),
+	              gs = as_input(g_scales, raw_scaling, "g_scales"), go = as_input(g_opacity, raw_scaling, "g_opacity"),
+	              gr = as_input(g_rotations, raw_scaling, "g_rotations");
+	torch::Tensor ds = torch::empty({P, 3}, s.options()), dop = torch::empty({P, 1}, s.options()), dr = torch::empty({P, 4}, s.options());
+	if (P)
+		check(rgs_activate_backward(P, s.data_ptr<float>(), o.data_ptr<float>(), r.data_ptr<float>(), f.data_ptr<float>(), gs.data_ptr<float>(),
+		                            go.data_ptr<float>(), gr.data_ptr<float>(), ds.data_ptr<float>(), dop.data_ptr<float>(), dr.data_ptr<float>(),
+		                            at::cuda::getCurrentCUDAStream().stream()));
+	return std::make_tuple(ds, dop, dr);
+}
+
+void DensificationStats(const torch::Tensor& means2D_grad, const torch::Tensor& radii, torch::Tensor& grad_accum, torch::Tensor& grad_accum_abs,
+                        torch::Tensor& grad_accum_abs_max, torch::Tensor& denom, torch::Tensor& max_radii2D) {
+	const c10::cuda::CUDAGuard guard(means2D_grad.device());
+	const int P = means2D_grad.size(0);
+	if (P == 0) return;
+	torch::Tensor g = as_input(means2D_grad, means2D_grad, "means2D.grad");
+	torch::Tensor rad = radii.contiguous();
+	for (const torch::Tensor* t : {&grad_accum, &grad_accum_abs, &grad_accum_abs_max, &denom})
+		TORCH_CHECK(t->is_contiguous() && t->scalar_type() == torch::kFloat32 && t->numel() == P, "densification statistics must be contiguous float32 [P,1] tensors");
+	float* mr = nullptr;
+	if (max_radii2D.numel() != 0) {
+		TORCH_CHECK(max_radii2D.is_contiguous() && max_radii2D.scalar_type() == torch::kFloat32 && max_radii2D.numel() == P, "max_radii2D must be contiguous float32 [P]");
+		mr = max_radii2D.data_ptr<float>();
+	}
+	check(rgs_densification_stats(P, g.data_ptr<float>(), rad.data_ptr<int>(), grad_accum.data_ptr<float>(), grad_accum_abs.data_ptr<float>(),
+	                              grad_accum_abs_max.data_ptr<float>(), denom.data_ptr<float>(), mr, at::cuda::getCurrentCUDAStream().stream()));
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -378,6 +431,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("rasterize_gaussians_slab", &RasterizeGaussiansSlabCUDA);
 	m.def("rasterize_gaussians_backward_render", &BackwardRenderCUDA);
 	m.def("rasterize_gaussians_backward_preprocess", &BackwardPreprocessCUDA);
+	m.def("activate_forward", &ActivateForward);
+	m.def("activate_backward", &ActivateBackward);
+	m.def("densification_stats", &DensificationStats);
 	m.def("grad_stride", [](bool require_coord, bool require_depth) { return rgs_grad_stride(require_coord, require_depth); });
 	m.def("launch_count", []() { return rgs_launch_count(); });
 	m.def("abi_version", []() { return rgs_abi_version(); });

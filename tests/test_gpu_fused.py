@@ -1,0 +1,156 @@
+"""Fused activations / densification statistics against the reference's torch expressions.
+
+The torch functions below restate reference scene/gaussian_model.py:156-166, :125-126, :743-747 and train.py:187-188 in
+plain fp32 eager torch (this is a floating-point kernel, so the checker is the torch fp32 reference of the same op).
+Tolerances: forward 2 ulp-ish (rel 1e-6), backward rel 1e-4 of the row-wise gradient scale (autograd sums the same
+terms in another order); the statistics are exact.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_activate(raw_scaling, raw_opacity, raw_rotation, filter_3D):
+    opacity = torch.sigmoid(raw_opacity)
+    scales = torch.exp(raw_scaling)
+    scales_square = torch.square(scales)
+    det1 = scales_square.prod(dim=1)
+    scales_after_square = scales_square + torch.square(filter_3D)
+    det2 = scales_after_square.prod(dim=1)
+    coef = torch.sqrt(det1 / det2)
+    return torch.sqrt(scales_after_square), opacity * coef[..., None], torch.nn.functional.normalize(raw_rotation)
+
+
+def _raw(P, seed, device="cuda"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    raw_scaling = (torch.randn(P, 3, generator=g) * 1.5 - 3.0).to(device)
+    raw_opacity = (torch.randn(P, 1, generator=g) * 2.0).to(device)
+    raw_rotation = torch.randn(P, 4, generator=g).to(device)
+    filter_3D = (torch.rand(P, 1, generator=g) * 0.05 + 1e-4).to(device)
+    return raw_scaling, raw_opacity, raw_rotation, filter_3D
+
+
+@pytest.mark.parametrize("P", [1, 257, 100_003])
+def test_activate_forward_matches_torch(P):
+    from rade_gs_b200.fused import activate_gaussians
+
+    raw = _raw(P, 11 + P)
+    s, o, r = activate_gaussians(*raw)
+    rs, ro, rr = _ref_activate(*raw)
+    assert s.shape == rs.shape and o.shape == ro.shape and r.shape == rr.shape
+    torch.testing.assert_close(s, rs, rtol=1e-6, atol=0)
+    torch.testing.assert_close(o, ro, rtol=2e-6, atol=1e-12)
+    torch.testing.assert_close(r, rr, rtol=1e-6, atol=1e-7)
+
+
+def test_activate_backward_matches_autograd():
+    from rade_gs_b200.fused import activate_gaussians
+
+    P = 50_021
+    raw = _raw(P, 5)
+    g = torch.Generator(device="cpu").manual_seed(99)
+    gs, go, gr = (torch.randn(P, k, generator=g).cuda() for k in (3, 1, 4))
+
+    def run(fn):
+        leaves = [t.clone().requires_grad_(True) for t in raw[:3]]
+        s, o, r = fn(*leaves, raw[3])
+        torch.autograd.backward([s, o, r], [gs, go, gr])
+        return [t.grad for t in leaves]
+
+    ours, ref = run(activate_gaussians), run(_ref_activate)
+    for a, b, name in zip(ours, ref, ("scaling", "opacity", "rotation")):
+        scale = b.abs().amax(dim=1, keepdim=True).clamp_min(1e-20)
+        err = ((a - b).abs() / scale).max().item()
+        assert err < 1e-4, f"d_raw_{name}: {err}"
+
+
+def test_activate_backward_partial_outputs():
+    """Only the opacity output is used downstream: autograd passes zeros for the rest."""
+    from rade_gs_b200.fused import activate_gaussians
+
+    raw = _raw(1000, 3)
+    leaves = [t.clone().requires_grad_(True) for t in raw[:3]]
+    _, o, _ = activate_gaussians(*leaves, raw[3])
+    o.sum().backward()
+    ref_leaves = [t.clone().requires_grad_(True) for t in raw[:3]]
+    _, ro, _ = _ref_activate(*ref_leaves, raw[3])
+    ro.sum().backward()
+    torch.testing.assert_close(leaves[1].grad, ref_leaves[1].grad, rtol=1e-4, atol=1e-9)
+    # d coef / d raw_scaling is the difference of two nearly equal chain-rule terms (through det1 and det2) of size
+    # ~|g o coef| <= 1: both sides carry ~1e-7 of cancellation noise, so the tolerance is absolute
+    torch.testing.assert_close(leaves[0].grad, ref_leaves[0].grad, rtol=1e-3, atol=2e-6)
+    assert leaves[2].grad.abs().max().item() == 0.0
+
+
+def test_activate_rejects_cpu_tensors():
+    from rade_gs_b200.fused import activate_gaussians
+
+    raw = _raw(8, 1, device="cpu")
+    with pytest.raises(RuntimeError):
+        activate_gaussians(*raw)
+
+
+def test_densification_stats_match_reference_expressions():
+    from rade_gs_b200.fused import add_densification_stats_
+
+    P = 70_001
+    g = torch.Generator(device="cpu").manual_seed(2)
+    grad = torch.randn(P, 3, generator=g).cuda() * 1e-3
+    radii = torch.randint(-1, 40, (P,), generator=g, dtype=torch.int32).cuda()
+    radii[radii < 0] = 0
+    state = [torch.rand(P, 1, generator=g).cuda() for _ in range(4)]
+    max_radii = (torch.rand(P, generator=g) * 30).cuda()
+
+    ref = [t.clone() for t in state]
+    ref_max = max_radii.clone()
+    vis = radii > 0
+    ref_max[vis] = torch.max(ref_max[vis], radii[vis])
+    ref[0][vis] += torch.norm(grad[vis, :2], dim=-1, keepdim=True)
+    ref[1][vis] += torch.norm(grad[vis, 2:], dim=-1, keepdim=True)
+    ref[2][vis] = torch.max(ref[2][vis], torch.norm(grad[vis, 2:], dim=-1, keepdim=True))
+    ref[3][vis] += 1
+
+    add_densification_stats_(grad, radii, state[0], state[1], state[2], state[3], max_radii)
+    torch.testing.assert_close(state[0], ref[0], rtol=2e-7, atol=0)
+    for a, b in zip(state[1:], ref[1:]):
+        assert torch.equal(a, b)
+    assert torch.equal(max_radii, ref_max)
+
+    # without the radius maximum
+    before = max_radii.clone()
+    add_densification_stats_(grad, radii, state[0], state[1], state[2], state[3])
+    assert torch.equal(max_radii, before)
+    assert torch.equal(state[3], ref[3] + vis[:, None].float())
+
+
+def test_fused_step_through_rasterizer():
+    """activate -> rasterize -> backward -> statistics as one training-step slice; gradients reach the raw parameters."""
+    import diff_gaussian_rasterization as dgr
+    from rade_gs_b200 import scenes
+    from rade_gs_b200.fused import activate_gaussians, add_densification_stats_
+    from test_gpu_api import _settings
+
+    sc, coord, depth = scenes.make_config("C1")
+    sc = sc.to("cuda")
+    P = sc.means3D.shape[0]
+    filter_3D = _raw(P, 21)[3] * 0.1
+    # raw parameters whose activations reproduce the synthetic scene (up to the 3D filter)
+    raw_scaling = torch.log(sc.scales.clamp_min(1e-6)).requires_grad_(True)
+    raw_opacity = torch.logit(sc.opacities.clamp(1e-4, 1 - 1e-4)).requires_grad_(True)
+    raw_rotation = (sc.rotations * 1.7).requires_grad_(True)
+    s, o, r = activate_gaussians(raw_scaling, raw_opacity, raw_rotation, filter_3D)
+    means2D = torch.zeros(P, 3, device="cuda", requires_grad=True)
+    out = dgr.GaussianRasterizer(_settings(dgr, sc, coord, depth, ks=0.1))(
+        means3D=sc.means3D, means2D=means2D, opacities=o, shs=sc.shs, scales=s, rotations=r)
+    color, radii = out[0], out[1]
+    color.mean().backward()
+    for t in (raw_scaling, raw_opacity, raw_rotation):
+        assert t.grad is not None and torch.isfinite(t.grad).all() and t.grad.abs().max() > 0
+    stats = [torch.zeros(P, 1, device="cuda") for _ in range(4)]
+    max_radii = torch.zeros(P, device="cuda")
+    add_densification_stats_(means2D.grad, radii, *stats, max_radii)
+    vis = radii > 0
+    assert vis.any()
+    assert torch.equal(stats[3][:, 0] > 0, vis)
+    assert torch.equal(max_radii, radii.float())
