@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RGS_ABI_VERSION 1
+#define RGS_ABI_VERSION 2
 
 typedef enum rgs_status {
 	RGS_OK = 0,
@@ -75,6 +75,10 @@ typedef struct rgs_gaussians {
 	const float* scales;         /* [P,3]   or NULL             */
 	const float* rotations;      /* [P,4]   or NULL (r,x,y,z)   */
 	const float* cov3D_precomp;  /* [P,6]   or NULL             */
+	/* ABI 2, opt-in: SH coefficients left in the two tensors the model stores them in
+	 * (GaussianModel._features_dc / _features_rest, scene/gaussian_model.py:133-136), sparing the per-iteration
+	 * torch.cat copy.  When shs_rest != NULL, `shs` is [P,1,3] (coefficient 0) and shs_rest [P,M-1,3]. */
+	const float* shs_rest;
 } rgs_gaussians;
 
 /* Forward outputs (rasterize_points.cu:71-78); maps of a variant that is switched off are zero-filled. */
@@ -130,6 +134,7 @@ typedef struct rgs_backward_out {
 	float* dL_dsh;        /* [P,M,3] or NULL when M == 0 */
 	float* dL_dscales;    /* [P,3] */
 	float* dL_drotations; /* [P,4] */
+	float* dL_dsh_rest;   /* ABI 2: [P,M-1,3] when the forward call passed shs_rest (then dL_dsh is [P,1,3]); else NULL */
 } rgs_backward_out;
 
 /* Floats per Gaussian of the screen-space gradient accumulator for a variant (16 or 32). */

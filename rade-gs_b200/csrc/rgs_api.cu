@@ -150,6 +150,8 @@ static int make_params(const rgs_camera* cam, const rgs_gaussians* g, FwdParams&
 	p.means3D = g->means3D;
 	p.opacities = g->opacities;
 	p.shs = g->shs;
+	p.shs_rest = has_sh ? g->shs_rest : nullptr;
+	if (p.shs_rest != nullptr && p.M < 2) return fail(RGS_E_INVALID, "shs_rest given but sh_coeffs < 2");
 	p.colors_precomp = g->colors_precomp;
 	p.scales = g->scales;
 	p.rotations = g->rotations;
@@ -299,7 +301,9 @@ int32_t rgs_backward_preprocess(const rgs_camera* cam, const rgs_gaussians* gs, 
 	if (p.P == 0) return RGS_OK;
 	if (!grad_accum || !out) return fail(RGS_E_INVALID, "null gradient accumulator / outputs");
 	cudaStream_t s = (cudaStream_t)cuda_stream;
-	ParamGradOut po{out->dL_dmeans2D, out->dL_dcolors, out->dL_dopacity, out->dL_dmeans3D, out->dL_dcov3D, out->dL_dsh, out->dL_dscales, out->dL_drotations};
+	ParamGradOut po{out->dL_dmeans2D, out->dL_dcolors, out->dL_dopacity, out->dL_dmeans3D, out->dL_dcov3D, out->dL_dsh, out->dL_dscales, out->dL_drotations, out->dL_dsh_rest};
+	if ((p.shs_rest != nullptr) != (po.d_sh_rest != nullptr) && po.d_sh != nullptr)
+		return fail(RGS_E_INVALID, "dL_dsh_rest must be given exactly when shs_rest is");
 	{ StageScope sc(ST_PREPROCESS_BWD, s); launch_preprocess_backward(p, g, in->radii, grad_accum, po, s); }
 	return debug_sync(cam, s, "backward preprocess");
 }

@@ -203,7 +203,7 @@ struct FwdParams {
 	int row_begin, row_end;   // slab of tile rows handled by this call
 	float tan_fovx, tan_fovy, focal_x, focal_y, kernel_size, scale_modifier;
 	bool coord, depth;        // variant (normal := coord || depth, forward.cu:732-739)
-	const float *means3D, *opacities, *shs, *colors_precomp, *scales, *rotations, *cov3D_precomp;
+	const float *means3D, *opacities, *shs, *shs_rest, *colors_precomp, *scales, *rotations, *cov3D_precomp;
 	const float *viewmatrix, *projmatrix, *cam_pos, *background;
 };
 
@@ -233,7 +233,7 @@ struct RenderGradIn {
 void launch_render_backward(const FwdParams& p, GeomView g, BinView b, ImgView img, RenderGradIn gin, float* grad_accum, cudaStream_t s);
 
 struct ParamGradOut {
-	float *d_means2D, *d_colors, *d_opacity, *d_means3D, *d_cov3D, *d_sh, *d_scales, *d_rotations;
+	float *d_means2D, *d_colors, *d_opacity, *d_means3D, *d_cov3D, *d_sh, *d_scales, *d_rotations, *d_sh_rest;
 };
 void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s);
 

@@ -16,15 +16,22 @@
 
 namespace rgs {
 
-// SH -> RGB (forward.cu:23-74).  `sh` points at this Gaussian's [M,3] block.
-__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ sh, float3 pos, float3 campos, uint8_t& clamp_bits) {
+// SH -> RGB (forward.cu:23-74).  `sh` points at this Gaussian's [M,3] block; with the split layout (`rest` != NULL)
+// `sh` is its [1,3] coefficient-0 row and `rest` its [M-1,3] block of the higher bands.
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ sh, const float* __restrict__ rest, float3 pos, float3 campos,
+                                            uint8_t& clamp_bits) {
 	float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
 	float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
 	dir.x /= len; dir.y /= len; dir.z /= len;
 
 	float c[48];
 	const int ncoef = (deg + 1) * (deg + 1);
-	if ((reinterpret_cast<uintptr_t>(sh) & 15) == 0) {
+	if (rest != nullptr) {
+		c[0] = __ldg(sh); c[1] = __ldg(sh + 1); c[2] = __ldg(sh + 2);
+#pragma unroll
+		for (int i = 3; i < 48; i++)
+			if (i < ncoef * 3) c[i] = __ldg(rest + i - 3);
+	} else if ((reinterpret_cast<uintptr_t>(sh) & 15) == 0) {
 		const float4* s4 = reinterpret_cast<const float4*>(sh);
 #pragma unroll
 		for (int i = 0; i < 12; i++) {
@@ -187,7 +194,10 @@ __global__ void __launch_bounds__(256, 3) preprocess_forward_kernel(FwdParams p,
 				uint8_t clamp_bits = 0;
 				if (p.colors_precomp == nullptr) {
 					const float3 campos = {p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]};
-					rgb = sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, p_orig, campos, clamp_bits);
+					if (p.shs_rest != nullptr)
+						rgb = sh_to_rgb(p.D, p.shs + (size_t)idx * 3, p.shs_rest + (size_t)idx * (p.M - 1) * 3, p_orig, campos, clamp_bits);
+					else
+						rgb = sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, nullptr, p_orig, campos, clamp_bits);
 				} else {
 					rgb = {p.colors_precomp[3 * idx], p.colors_precomp[3 * idx + 1], p.colors_precomp[3 * idx + 2]};
 				}

@@ -362,10 +362,41 @@ __global__ void __launch_bounds__(128, 4) preprocess_backward_kernel(FwdParams p
 // an odd number of floats: conflict-free), overwrites it in place with dL_dsh, and the block streams back coalesced.
 // The view-direction term is added to dL_dmeans3D (third part of the mean gradient, backward.cu:131-139).
 constexpr int SH_WARPS = 8;
+
+// `count` rows of `width` floats, contiguous in global memory, <-> columns [col0, col0 + width) of the padded shared tile
+template <bool TO_SHARED>
+__device__ __forceinline__ void sh_block_copy(float* tile, int stride, int col0, int width, int count, const float* src, float* dst, int lane) {
+	const int total = count * width;
+	const uintptr_t addr = TO_SHARED ? reinterpret_cast<uintptr_t>(src) : reinterpret_cast<uintptr_t>(dst);
+	if ((addr & 15) == 0 && (total & 3) == 0) {
+		for (int e = lane * 4; e < total; e += 128) {
+			float vv[4];
+			if (TO_SHARED) {
+				const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
+				vv[0] = v.x; vv[1] = v.y; vv[2] = v.z; vv[3] = v.w;
+			}
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int r = (e + q) / width, c = (e + q) - r * width;
+				if (TO_SHARED) tile[r * stride + col0 + c] = vv[q];
+				else vv[q] = tile[r * stride + col0 + c];
+			}
+			if (!TO_SHARED) *reinterpret_cast<float4*>(dst + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+		}
+	} else {
+		for (int e = lane; e < total; e += 32) {
+			const int r = e / width, c = e - r * width;
+			if (TO_SHARED) tile[r * stride + col0 + c] = __ldg(src + e);
+			else dst[e] = tile[r * stride + col0 + c];
+		}
+	}
+}
+
 __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_kernel(int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ cam_pos,
-                                                                     const float* __restrict__ shs, const int* __restrict__ radii,
-                                                                     const uint8_t* __restrict__ clamped, const float* __restrict__ grad_accum, int GF,
-                                                                     float* __restrict__ d_sh, float* __restrict__ d_means3D) {
+                                                                     const float* __restrict__ shs, const float* __restrict__ shs_rest,
+                                                                     const int* __restrict__ radii, const uint8_t* __restrict__ clamped,
+                                                                     const float* __restrict__ grad_accum, int GF, float* __restrict__ d_sh,
+                                                                     float* __restrict__ d_sh_rest, float* __restrict__ d_means3D) {
 	extern __shared__ float s_sh[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int row = 3 * M, stride = row | 1;
@@ -373,26 +404,11 @@ __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_kernel(int P, int D
 	const int g0 = (blockIdx.x * SH_WARPS + warp) * 32;
 	if (g0 >= P) return;
 	const int count = min(32, P - g0);
-	const int total = count * row;
-	const float* src = shs + (size_t)g0 * row;
-	float* dst = d_sh + (size_t)g0 * row;
-	const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && (total & 3) == 0;
-	if (vec) {
-		for (int e = lane * 4; e < total; e += 128) {
-			const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
-			const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-			for (int q = 0; q < 4; q++) {
-				const int r = (e + q) / row, c = (e + q) - r * row;
-				tile[r * stride + c] = vv[q];
-			}
-		}
-	} else {
-		for (int e = lane; e < total; e += 32) {
-			const int r = e / row, c = e - r * row;
-			tile[r * stride + c] = __ldg(src + e);
-		}
-	}
+	// split layout (ABI 2): coefficient 0 comes from / goes to the [P,1,3] tensors, bands 1.. the [P,M-1,3] ones
+	const bool split = shs_rest != nullptr;
+	const int w0 = split ? 3 : row;
+	sh_block_copy<true>(tile, stride, 0, w0, count, shs + (size_t)g0 * w0, nullptr, lane);
+	if (split) sh_block_copy<true>(tile, stride, 3, row - 3, count, shs_rest + (size_t)g0 * (row - 3), nullptr, lane);
 	__syncwarp();
 	const int idx = g0 + lane;
 	if (lane < count) {
@@ -466,22 +482,8 @@ __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_kernel(int P, int D
 		}
 	}
 	__syncwarp();
-	if (vec) {
-		for (int e = lane * 4; e < total; e += 128) {
-			float vv[4];
-#pragma unroll
-			for (int q = 0; q < 4; q++) {
-				const int r = (e + q) / row, c = (e + q) - r * row;
-				vv[q] = tile[r * stride + c];
-			}
-			*reinterpret_cast<float4*>(dst + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-		}
-	} else {
-		for (int e = lane; e < total; e += 32) {
-			const int r = e / row, c = e - r * row;
-			dst[e] = tile[r * stride + c];
-		}
-	}
+	sh_block_copy<false>(tile, stride, 0, w0, count, nullptr, d_sh + (size_t)g0 * w0, lane);
+	if (split) sh_block_copy<false>(tile, stride, 3, row - 3, count, nullptr, d_sh_rest + (size_t)g0 * (row - 3), lane);
 }
 
 void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s) {
@@ -494,8 +496,9 @@ void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii
 		static size_t configured[64] = {};
 		if (smem > 48 * 1024) ensure_dynamic_smem(sh_backward_kernel, smem, configured);
 		const int per_block = SH_WARPS * 32;
-		sh_backward_kernel<<<(p.P + per_block - 1) / per_block, per_block, smem, s>>>(p.P, p.D, p.M, p.means3D, p.cam_pos, p.shs, radii, g.clamped,
-		                                                                               grad_accum, grad_floats(p.coord), out.d_sh, out.d_means3D);
+		sh_backward_kernel<<<(p.P + per_block - 1) / per_block, per_block, smem, s>>>(p.P, p.D, p.M, p.means3D, p.cam_pos, p.shs, p.shs_rest, radii,
+		                                                                               g.clamped, grad_accum, grad_floats(p.coord), out.d_sh, out.d_sh_rest,
+		                                                                               out.d_means3D);
 		count_launch();
 	}
 }

@@ -77,12 +77,13 @@ void fill_camera(CamHolder& h, const torch::Tensor& like, const torch::Tensor& b
 }
 
 struct GaussHolder {
-	torch::Tensor means, opac, sh, colors, scales, rots, cov;
+	torch::Tensor means, opac, sh, sh_rest, colors, scales, rots, cov;
 	rgs_gaussians g;
 };
 
 void fill_gaussians(GaussHolder& h, const torch::Tensor& means3D, const torch::Tensor& opacity, const torch::Tensor& sh, const torch::Tensor& colors,
-                    const torch::Tensor& scales, const torch::Tensor& rotations, const torch::Tensor& cov3D_precomp) {
+                    const torch::Tensor& scales, const torch::Tensor& rotations, const torch::Tensor& cov3D_precomp,
+                    const torch::Tensor& sh_rest = torch::Tensor()) {
 	h.means = as_input(means3D, means3D, "means3D");
 	h.opac = as_input(opacity, means3D, "opacity");
 	h.sh = as_input(sh, means3D, "sh");
@@ -98,6 +99,21 @@ void fill_gaussians(GaussHolder& h, const torch::Tensor& means3D, const torch::T
 	h.g.scales = opt_ptr(h.scales);
 	h.g.rotations = opt_ptr(h.rots);
 	h.g.cov3D_precomp = opt_ptr(h.cov);
+	h.g.shs_rest = nullptr;
+	if (sh_rest.defined() && sh_rest.numel() != 0) {  // split layout: `sh` is [P,1,3], sh_rest [P,M-1,3]
+		TORCH_CHECK(sh.dim() == 3 && sh.size(1) == 1 && sh_rest.dim() == 3 && sh_rest.size(0) == sh.size(0) && sh_rest.size(2) == 3,
+		            "split SH layout needs shs_dc [P,1,3] and shs_rest [P,M-1,3]");
+		h.sh_rest = as_input(sh_rest, means3D, "shs_rest");
+		h.g.shs_rest = h.sh_rest.data_ptr<float>();
+	}
+}
+
+// number of SH coefficients per Gaussian for either layout
+int sh_coeffs(const torch::Tensor& sh, const torch::Tensor& sh_rest) {
+	int M = 0;
+	if (sh.size(0) != 0) M = sh.size(1);
+	if (sh_rest.defined() && sh_rest.numel() != 0) M += sh_rest.size(1);
+	return M;
 }
 
 using FwdResult = std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
@@ -108,7 +124,7 @@ FwdResult forward_impl(const torch::Tensor& background, const torch::Tensor& mea
                        const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
                        const float kernel_size, const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
                        const torch::Tensor& campos, const bool prefiltered, const bool require_coord, const bool require_depth, const bool debug,
-                       int row_begin, int row_end) {
+                       int row_begin, int row_end, const torch::Tensor& sh_rest = torch::Tensor()) {
 	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
 		AT_ERROR("means3D must have dimensions (num_points, 3)");
 	}
@@ -130,13 +146,12 @@ FwdResult forward_impl(const torch::Tensor& background, const torch::Tensor& mea
 
 	int rendered = 0;
 	if (P != 0) {
-		int M = 0;
-		if (sh.size(0) != 0) M = sh.size(1);
+		const int M = sh_coeffs(sh, sh_rest);
 		CamHolder ch;
 		fill_camera(ch, means3D, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, kernel_size, scale_modifier, H, W, degree, M,
 		            prefiltered, require_coord, require_depth, debug, row_begin, row_end);
 		GaussHolder gh;
-		fill_gaussians(gh, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp);
+		fill_gaussians(gh, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp, sh_rest);
 		rgs_forward_out fo{out_color.data_ptr<float>(), out_coord.data_ptr<float>(), out_mcoord.data_ptr<float>(), out_alpha.data_ptr<float>(),
 		                   out_normal.data_ptr<float>(), out_depth.data_ptr<float>(), out_mdepth.data_ptr<float>(), radii.data_ptr<int>()};
 		rgs_buffers bufs{resize_cb, &geomBuffer, resize_cb, &binningBuffer, resize_cb, &imgBuffer};
@@ -176,14 +191,13 @@ void fill_backward(BackwardCtx& c, const torch::Tensor& background, const torch:
                    const torch::Tensor& dL_dout_alpha, const torch::Tensor& dL_dout_normal, const torch::Tensor& normalmap, const torch::Tensor& sh,
                    const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
                    const torch::Tensor& imageBuffer, const torch::Tensor& alphas, const bool require_coord, const bool require_depth,
-                   const bool debug, int row_begin, int row_end) {
+                   const bool debug, int row_begin, int row_end, const torch::Tensor& sh_rest = torch::Tensor()) {
 	const int H = dL_dout_color.size(1), W = dL_dout_color.size(2);
-	int M = 0;
-	if (sh.size(0) != 0) M = sh.size(1);
+	const int M = sh_coeffs(sh, sh_rest);
 	fill_camera(c.ch, means3D, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, kernel_size, scale_modifier, H, W, degree, M, false,
 	            require_coord, require_depth, debug, row_begin, row_end);
 	torch::Tensor no_opacity = torch::empty({0});  // backward does not receive the opacities (rasterize_points.h:43-76)
-	fill_gaussians(c.gh, means3D, no_opacity, sh, colors, scales, rotations, cov3D_precomp);
+	fill_gaussians(c.gh, means3D, no_opacity, sh, colors, scales, rotations, cov3D_precomp, sh_rest);
 	c.g_color = as_input(dL_dout_color, means3D, "dL_dout_color");
 	c.g_coord = as_input(dL_dout_coord, means3D, "dL_dout_coord");
 	c.g_mcoord = as_input(dL_dout_mcoord, means3D, "dL_dout_mcoord");
@@ -216,11 +230,11 @@ void fill_backward(BackwardCtx& c, const torch::Tensor& background, const torch:
 using BwdResult = std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>;
 
 struct GradTensors {
-	torch::Tensor means3D, means2D, colors, opacity, cov3D, sh, scales, rotations;
+	torch::Tensor means3D, means2D, colors, opacity, cov3D, sh, sh_rest, scales, rotations;
 	rgs_backward_out out;
 };
 
-void alloc_grads(GradTensors& t, const torch::Tensor& means3D, int P, int M) {
+void alloc_grads(GradTensors& t, const torch::Tensor& means3D, int P, int M, bool split_sh = false) {
 	auto o = means3D.options();
 	auto mk = [&](std::initializer_list<int64_t> shape) { return P == 0 ? torch::zeros(shape, o) : torch::empty(shape, o); };
 	t.means3D = mk({P, 3});
@@ -228,7 +242,8 @@ void alloc_grads(GradTensors& t, const torch::Tensor& means3D, int P, int M) {
 	t.colors = mk({P, 3});
 	t.opacity = mk({P, 1});
 	t.cov3D = mk({P, 6});
-	t.sh = mk({P, M, 3});
+	t.sh = mk({P, split_sh ? 1 : M, 3});
+	if (split_sh) t.sh_rest = mk({P, M - 1, 3});
 	t.scales = mk({P, 3});
 	t.rotations = mk({P, 4});
 	t.out.dL_dmeans2D = t.means2D.data_ptr<float>();
@@ -239,6 +254,7 @@ void alloc_grads(GradTensors& t, const torch::Tensor& means3D, int P, int M) {
 	t.out.dL_dsh = M > 0 ? t.sh.data_ptr<float>() : nullptr;
 	t.out.dL_dscales = t.scales.data_ptr<float>();
 	t.out.dL_drotations = t.rotations.data_ptr<float>();
+	t.out.dL_dsh_rest = split_sh ? t.sh_rest.data_ptr<float>() : nullptr;
 }
 
 BwdResult RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
@@ -367,6 +383,51 @@ BwdResult BackwardPreprocessCUDA(const torch::Tensor& grad_accum, const torch::T
 	return std::make_tuple(gt.means2D, gt.colors, gt.opacity, gt.means3D, gt.cov3D, gt.sh, gt.scales, gt.rotations);
 }
 
+// ---- split SH layout (opt-in): features_dc / features_rest stay two tensors, no torch.cat per iteration ----
+
+FwdResult RasterizeGaussiansSplitShCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                                        const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                        const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                        const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const float kernel_size,
+                                        const int image_height, const int image_width, const torch::Tensor& sh_dc, const torch::Tensor& sh_rest,
+                                        const int degree, const torch::Tensor& campos, const bool prefiltered, const bool require_coord,
+                                        const bool require_depth, const bool debug) {
+	return forward_impl(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+	                    tan_fovy, kernel_size, image_height, image_width, sh_dc, degree, campos, prefiltered, require_coord, require_depth, debug, 0,
+	                    -1, sh_rest);
+}
+
+using BwdSplitResult = std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+                                  torch::Tensor, torch::Tensor>;
+
+// returns (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh_dc, dL_dsh_rest, dL_dscales, dL_drotations)
+BwdSplitResult RasterizeGaussiansBackwardSplitShCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii, const torch::Tensor& colors,
+    const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+    const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const float kernel_size,
+    const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_coord, const torch::Tensor& dL_dout_mcoord, const torch::Tensor& dL_dout_depth,
+    const torch::Tensor& dL_dout_mdepth, const torch::Tensor& dL_dout_alpha, const torch::Tensor& dL_dout_normal, const torch::Tensor& normalmap,
+    const torch::Tensor& sh_dc, const torch::Tensor& sh_rest, const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer,
+    const int R, const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const torch::Tensor& alphas, const bool require_coord,
+    const bool require_depth, const bool debug) {
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor: this rasterizer has no CPU path");
+	TORCH_CHECK(sh_rest.defined() && sh_rest.numel() != 0, "split SH layout needs a non-empty shs_rest");
+	const c10::cuda::CUDAGuard guard(means3D.device());
+	const int P = means3D.size(0);
+	GradTensors gt;
+	alloc_grads(gt, means3D, P, sh_coeffs(sh_dc, sh_rest), true);
+	if (P != 0) {
+		BackwardCtx c;
+		fill_backward(c, background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+		              tan_fovy, kernel_size, dL_dout_color, dL_dout_coord, dL_dout_mcoord, dL_dout_depth, dL_dout_mdepth, dL_dout_alpha,
+		              dL_dout_normal, normalmap, sh_dc, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, alphas, require_coord,
+		              require_depth, debug, 0, -1, sh_rest);
+		torch::Tensor scratch = torch::empty({0}, means3D.options().dtype(torch::kByte));
+		check(rgs_backward(&c.ch.cam, &c.gh.g, &c.in, &gt.out, resize_cb, &scratch, at::cuda::getCurrentCUDAStream().stream()));
+	}
+	return std::make_tuple(gt.means2D, gt.colors, gt.opacity, gt.means3D, gt.cov3D, gt.sh, gt.sh_rest, gt.scales, gt.rotations);
+}
+
 // ---- fused activations / densification statistics (opt-in) --------------------------------------------
 
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> ActivateForward(const torch::Tensor& raw_scaling, const torch::Tensor& raw_opacity,
@@ -394,6 +455,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> ActivateBackward(const t
 	              r = as_input(raw_rotation, raw_scaling, "raw_rotation"), f = as_input(filter_3D, raw_scaling, "filter_3D"),
 	              gs = as_input(g_scales, raw_scaling, "g_scales"), go = as_input(g_opacity, raw_scaling, "g_opacity"),
 	              gr = as_input(g_rotations, raw_scaling, "g_rotations");
+	TORCH_CHECK(gs.numel() == 3 * (int64_t)P && go.numel() == P && gr.numel() == 4 * (int64_t)P, "activate backward: gradient shapes must be [P,3] [P,1] [P,4]");
 	torch::Tensor ds = torch::empty({P, 3}, s.options()), dop = torch::empty({P, 1}, s.options()), dr = torch::empty({P, 4}, s.options());
 	if (P)
 		check(rgs_activate_backward(P, s.data_ptr<float>(), o.data_ptr<float>(), r.data_ptr<float>(), f.data_ptr<float>(), gs.data_ptr<float>(),
@@ -431,6 +493,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("rasterize_gaussians_slab", &RasterizeGaussiansSlabCUDA);
 	m.def("rasterize_gaussians_backward_render", &BackwardRenderCUDA);
 	m.def("rasterize_gaussians_backward_preprocess", &BackwardPreprocessCUDA);
+	m.def("rasterize_gaussians_split_sh", &RasterizeGaussiansSplitShCUDA);
+	m.def("rasterize_gaussians_backward_split_sh", &RasterizeGaussiansBackwardSplitShCUDA);
 	m.def("activate_forward", &ActivateForward);
 	m.def("activate_backward", &ActivateBackward);
 	m.def("densification_stats", &DensificationStats);

@@ -111,6 +111,43 @@ class _RasterizeGaussians(torch.autograd.Function):
         return g_means3D, g_means2D, g_sh, g_colors, g_opacities, g_scales, g_rotations, g_cov3D, None
 
 
+class _RasterizeGaussiansSplitSh(torch.autograd.Function):
+    """Same op with the SH coefficients left in the model's two tensors (``_features_dc`` [P,1,3], ``_features_rest``
+    [P,M-1,3]; reference scene/gaussian_model.py:133-136 concatenates them every iteration).  Opt-in extension
+    (SURVEY.md 8f row 1): pass ``shs=(features_dc, features_rest)`` to ``GaussianRasterizer.forward``."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh_dc, sh_rest, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+        s = raster_settings
+        none = _absent()
+        args = (
+            s.bg, means3D, none, opacities, scales, rotations, s.scale_modifier, cov3Ds_precomp,
+            s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size, s.image_height, s.image_width,
+            sh_dc, sh_rest, s.sh_degree, s.campos, s.prefiltered, s.require_coord, s.require_depth, s.debug,
+        )
+        (num_rendered, color, coord, mcoord, alpha, normal, depth, mdepth, radii,
+         geom_buf, binning_buf, img_buf) = _call_with_dump(_C.rasterize_gaussians_split_sh, args, s.debug, "snapshot_fw.dump", "forward")
+        ctx.raster_settings = s
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(means3D, scales, rotations, cov3Ds_precomp, normal, radii, sh_dc, sh_rest, geom_buf, binning_buf, img_buf, alpha)
+        return color, radii, coord, mcoord, depth, mdepth, alpha, normal
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_coord, grad_mcoord, grad_depth, grad_mdepth, grad_alpha, grad_normal):
+        s = ctx.raster_settings
+        (means3D, scales, rotations, cov3Ds_precomp, normal, radii, sh_dc, sh_rest, geom_buf, binning_buf, img_buf, alpha) = ctx.saved_tensors
+        args = (
+            s.bg, means3D, radii, _absent(), scales, rotations, s.scale_modifier, cov3Ds_precomp,
+            s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size,
+            grad_color, grad_coord, grad_mcoord, grad_depth, grad_mdepth, grad_alpha, grad_normal, normal,
+            sh_dc, sh_rest, s.sh_degree, s.campos, geom_buf, ctx.num_rendered, binning_buf, img_buf, alpha,
+            s.require_coord, s.require_depth, s.debug,
+        )
+        (g_means2D, _g_colors, g_opacities, g_means3D, g_cov3D, g_sh_dc, g_sh_rest, g_scales, g_rotations) = _call_with_dump(
+            _C.rasterize_gaussians_backward_split_sh, args, s.debug, "snapshot_bw.dump", "backward")
+        return g_means3D, g_means2D, g_sh_dc, g_sh_rest, g_opacities, g_scales, g_rotations, g_cov3D, None
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
 
@@ -142,11 +179,20 @@ class GaussianRasterizer(nn.Module):
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None):
         _check_exclusive(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        split_sh = isinstance(shs, (tuple, list))  # extension: (features_dc [P,1,3], features_rest [P,M-1,3])
         shs = _absent() if shs is None else shs
         colors_precomp = _absent() if colors_precomp is None else colors_precomp
         scales = _absent() if scales is None else scales
         rotations = _absent() if rotations is None else rotations
         cov3D_precomp = _absent() if cov3D_precomp is None else cov3D_precomp
+        if split_sh:
+            if len(shs) != 2:
+                raise ValueError("split SH layout: shs must be the pair (features_dc, features_rest)")
+            if shs[1].numel() == 0:  # degree-0 model: nothing to split
+                shs = shs[0]
+            else:
+                return _RasterizeGaussiansSplitSh.apply(means3D, means2D, shs[0], shs[1], opacities, scales, rotations, cov3D_precomp,
+                                                        self.raster_settings)
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, self.raster_settings)
 
     def integrate(self, points3D, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,

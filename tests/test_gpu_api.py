@@ -113,7 +113,8 @@ def test_c_abi_direct_call_with_raw_pointers():
 
     class Gs(ctypes.Structure):
         _fields_ = [("P", ctypes.c_int32), ("means3D", ctypes.c_void_p), ("opacities", ctypes.c_void_p), ("shs", ctypes.c_void_p),
-                    ("colors_precomp", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p), ("cov3D_precomp", ctypes.c_void_p)]
+                    ("colors_precomp", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p), ("cov3D_precomp", ctypes.c_void_p),
+                    ("shs_rest", ctypes.c_void_p)]
 
     class Out(ctypes.Structure):
         _fields_ = [(n, ctypes.c_void_p) for n in ("out_color", "out_coord", "out_mcoord", "out_alpha", "out_normal", "out_depth", "out_mdepth", "radii")]

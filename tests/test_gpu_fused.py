@@ -154,3 +154,42 @@ def test_fused_step_through_rasterizer():
     assert vis.any()
     assert torch.equal(stats[3][:, 0] > 0, vis)
     assert torch.equal(max_radii, radii.float())
+
+
+@pytest.mark.parametrize("deg,M", [(3, 16), (1, 4), (2, 16)])
+def test_split_sh_layout_is_bit_identical_to_concatenated(deg, M):
+    """shs=(features_dc, features_rest) must give the same bits as shs=torch.cat(...) (gaussian_model.py:133-136)."""
+    import diff_gaussian_rasterization as dgr
+    from rade_gs_b200 import scenes
+    from test_gpu_api import _settings
+
+    sc, coord, depth = scenes.make_config("C1")
+    sc = sc.to("cuda")
+    P = sc.means3D.shape[0] - 13  # ragged last warp in the SH kernel
+    dc = sc.shs[:P, :1].contiguous()
+    rest = sc.shs[:P, 1:M].contiguous()
+    up = scenes.make_upstream_grads(sc.height, sc.width, device="cuda")
+
+    def run(split):
+        leaves = {k: getattr(sc, k)[:P].clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities")}
+        f_dc, f_rest = dc.clone().requires_grad_(True), rest.clone().requires_grad_(True)
+        shs = (f_dc, f_rest) if split else torch.cat((f_dc, f_rest), dim=1)
+        means2D = torch.zeros(P, 3, device="cuda", requires_grad=True)
+        out = dgr.GaussianRasterizer(_settings(dgr, sc, coord, depth, ks=0.1, deg=deg))(
+            means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=shs, scales=leaves["scales"],
+            rotations=leaves["rotations"])
+        color, radii, _, _, d, md, alpha, normal = out
+        loss = (color * up["color"]).sum() + (d * up["depth"]).sum() + (alpha * up["alpha"]).sum() + (normal * up["normal"]).sum()
+        loss.backward()
+        return [o.detach() for o in out], f_dc.grad, f_rest.grad, leaves["means3D"].grad
+
+    o_cat, dc_cat, rest_cat, m_cat = run(False)
+    o_spl, dc_spl, rest_spl, m_spl = run(True)
+    for a, b in zip(o_cat, o_spl):
+        assert torch.equal(a, b)
+    assert dc_spl.shape == dc.shape and rest_spl.shape == rest.shape
+    # per-Gaussian SH arithmetic is identical; only the screen-space accumulation order (atomics) differs run to run
+    torch.testing.assert_close(dc_spl, dc_cat, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(rest_spl, rest_cat, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(m_spl, m_cat, rtol=1e-3, atol=1e-4)
+    assert rest_spl.abs().max() > 0 and dc_spl.abs().max() > 0
