@@ -175,6 +175,25 @@ int32_t rgs_densification_stats(int32_t P, const float* means2D_grad, const int3
                                 float* grad_accum_abs, float* grad_accum_abs_max, float* denom, float* max_radii2D,
                                 void* cuda_stream);
 
+/* ---- image-side consumers of the maps, opt-in ----
+ * rgs_ssim_l1_forward: utils/loss_utils.py:17-18 and :35-63 over `planes` [H,W] fp32 planes.  sums[0] = sum of the SSIM map,
+ *   sums[1] = sum |img - gt| (the call zeroes them; divide by planes*H*W for the means).  dmaps ([3,planes,H,W], may be NULL
+ *   for evaluation) receives the partial derivatives of the SSIM map that rgs_ssim_l1_backward needs.
+ * rgs_ssim_l1_backward: d_img = upstream * (w_ssim * d(sum SSIM map)/d img + w_l1 * sign(img - gt)); upstream is a DEVICE
+ *   scalar or NULL (1.0).  For train.py:163's loss: w_ssim = -lambda_dssim / n, w_l1 = (1 - lambda_dssim) / n.
+ * rgs_normal_consistency: train.py:143-156 with utils/graphics_utils.py:97-126.  from_depth != 0: the two maps are [1,H,W]
+ *   depth maps, back-projected with rays ((x+0.5)*inv_fx + cx, (y+0.5)*inv_fy + cy, 1); else they are [3,H,W] point maps.
+ *   loss_sum = sum over pixels of w_expected*(1 - <normal, n_expected>) + w_median*(1 - <normal, n_median>) (zeroed by the call);
+ *   d_normal [3,H,W], d_expected / d_median (shaped like the maps) are fully written. */
+int32_t rgs_ssim_l1_forward(int32_t planes, int32_t H, int32_t W, const float* img, const float* gt, float* dmaps, double* sums,
+                            void* cuda_stream);
+int32_t rgs_ssim_l1_backward(int32_t planes, int32_t H, int32_t W, const float* img, const float* gt, const float* dmaps,
+                             float w_ssim, float w_l1, const float* upstream, float* d_img, void* cuda_stream);
+int32_t rgs_normal_consistency(int32_t H, int32_t W, int32_t from_depth, float inv_fx, float inv_fy, float cx, float cy,
+                               const float* rendered_normal, const float* map_expected, const float* map_median,
+                               float w_expected, float w_median, double* loss_sum, float* d_normal, float* d_expected,
+                               float* d_median, void* cuda_stream);
+
 /* Introspection for parity tests: views into the private buffers written by rgs_forward
  * (the reference keeps the same data at BinningState::point_list / ImageState::ranges,
  * rasterizer_impl.cu:237-250,224-235).  Pointers are device addresses inside the given buffers. */

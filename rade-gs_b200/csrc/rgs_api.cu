@@ -365,6 +365,38 @@ int32_t rgs_densification_stats(int32_t P, const float* means2D_grad, const int3
 	return e == cudaSuccess ? (int32_t)RGS_OK : fail(RGS_E_CUDA, cudaGetErrorString(e));
 }
 
+static int32_t after_launch() {
+	cudaError_t e = cudaGetLastError();
+	return e == cudaSuccess ? (int32_t)RGS_OK : fail(RGS_E_CUDA, cudaGetErrorString(e));
+}
+
+int32_t rgs_ssim_l1_forward(int32_t planes, int32_t H, int32_t W, const float* img, const float* gt, float* dmaps, double* sums, void* cuda_stream) {
+	if (planes < 0 || H <= 0 || W <= 0) return fail(RGS_E_INVALID, "image size must be positive");
+	if (!img || !gt || !sums) return fail(RGS_E_INVALID, "null pointer");
+	if (planes > 65535) return fail(RGS_E_INVALID, "too many image planes");
+	launch_ssim_l1_forward(planes, H, W, img, gt, dmaps, sums, (cudaStream_t)cuda_stream);
+	return after_launch();
+}
+
+int32_t rgs_ssim_l1_backward(int32_t planes, int32_t H, int32_t W, const float* img, const float* gt, const float* dmaps, float w_ssim, float w_l1,
+                             const float* upstream, float* d_img, void* cuda_stream) {
+	if (planes < 0 || H <= 0 || W <= 0) return fail(RGS_E_INVALID, "image size must be positive");
+	if (!img || !gt || !dmaps || !d_img) return fail(RGS_E_INVALID, "null pointer");
+	if (planes > 65535) return fail(RGS_E_INVALID, "too many image planes");
+	launch_ssim_l1_backward(planes, H, W, img, gt, dmaps, w_ssim, w_l1, upstream, d_img, (cudaStream_t)cuda_stream);
+	return after_launch();
+}
+
+int32_t rgs_normal_consistency(int32_t H, int32_t W, int32_t from_depth, float inv_fx, float inv_fy, float cx, float cy, const float* rendered_normal,
+                               const float* map_expected, const float* map_median, float w_expected, float w_median, double* loss_sum,
+                               float* d_normal, float* d_expected, float* d_median, void* cuda_stream) {
+	if (H <= 0 || W <= 0) return fail(RGS_E_INVALID, "image size must be positive");
+	if (!rendered_normal || !map_expected || !map_median || !loss_sum || !d_normal || !d_expected || !d_median) return fail(RGS_E_INVALID, "null pointer");
+	launch_normal_consistency(H, W, from_depth != 0, inv_fx, inv_fy, cx, cy, rendered_normal, map_expected, map_median, w_expected, w_median, loss_sum,
+	                          d_normal, d_expected, d_median, (cudaStream_t)cuda_stream);
+	return after_launch();
+}
+
 int32_t rgs_debug_get_views(const rgs_camera* cam, int32_t P, int64_t num_rendered, const char* geom_buffer, const char* binning_buffer,
                             const char* image_buffer, rgs_debug_views* views) {
 	if (!cam || !views) return fail(RGS_E_INVALID, "null pointer");

@@ -246,4 +246,12 @@ void launch_activate_backward(int P, const float* raw_scaling, const float* raw_
 void launch_densification_stats(int P, const float* means2D_grad, const int* radii, float* grad_accum, float* grad_accum_abs, float* grad_accum_abs_max,
                                 float* denom, float* max_radii2D, cudaStream_t s);
 
+// fused image-side losses (rgs_image_loss.cu)
+void launch_ssim_l1_forward(int planes, int H, int W, const float* img, const float* gt, float* dmaps, double* sums, cudaStream_t s);
+void launch_ssim_l1_backward(int planes, int H, int W, const float* img, const float* gt, const float* dmaps, float w_ssim, float w_l1,
+                             const float* upstream, float* d_img, cudaStream_t s);
+void launch_normal_consistency(int H, int W, bool from_depth, float inv_fx, float inv_fy, float cx, float cy, const float* rendered_normal,
+                               const float* map_e, const float* map_m, float w_e, float w_m, double* loss_sum, float* d_normal, float* d_e, float* d_m,
+                               cudaStream_t s);
+
 }  // namespace rgs

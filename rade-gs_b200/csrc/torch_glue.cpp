@@ -482,6 +482,72 @@ void DensificationStats(const torch::Tensor& means2D_grad, const torch::Tensor& 
 	                              grad_accum_abs_max.data_ptr<float>(), denom.data_ptr<float>(), mr, at::cuda::getCurrentCUDAStream().stream()));
 }
 
+// ---- fused image-side losses (opt-in) -----------------------------------------------------------------
+
+torch::Tensor image_input(const torch::Tensor& t, const torch::Tensor& like, const char* name) {
+	TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor: no CPU path");
+	TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be float32");
+	TORCH_CHECK(t.device() == like.device(), name, " must be on the same device as the image");
+	return t.contiguous();
+}
+
+// returns (sums [2] float64: sum of the SSIM map, sum |img - gt|; dmaps [3, planes, H, W] or empty)
+std::tuple<torch::Tensor, torch::Tensor> SsimL1Forward(const torch::Tensor& img, const torch::Tensor& gt, const bool need_grad) {
+	TORCH_CHECK(img.dim() >= 2 && img.numel() == gt.numel() && img.size(-1) == gt.size(-1) && img.size(-2) == gt.size(-2),
+	            "ssim: images must have the same number of elements and the same [H, W]");
+	torch::Tensor a = image_input(img, img, "img1"), b = image_input(gt, img, "img2");
+	const c10::cuda::CUDAGuard guard(a.device());
+	const int H = a.size(-2), W = a.size(-1);
+	const int planes = (int)(a.numel() / ((int64_t)H * W));
+	torch::Tensor sums = torch::empty({2}, a.options().dtype(torch::kFloat64));
+	torch::Tensor dmaps = need_grad ? torch::empty({3, planes, H, W}, a.options()) : torch::empty({0}, a.options());
+	check(rgs_ssim_l1_forward(planes, H, W, a.data_ptr<float>(), b.data_ptr<float>(), need_grad ? dmaps.data_ptr<float>() : nullptr,
+	                          sums.data_ptr<double>(), at::cuda::getCurrentCUDAStream().stream()));
+	return std::make_tuple(sums, dmaps);
+}
+
+torch::Tensor SsimL1Backward(const torch::Tensor& img, const torch::Tensor& gt, const torch::Tensor& dmaps, const double w_ssim, const double w_l1,
+                             const torch::Tensor& upstream) {
+	torch::Tensor a = image_input(img, img, "img1"), b = image_input(gt, img, "img2"), d = image_input(dmaps, img, "dmaps");
+	const c10::cuda::CUDAGuard guard(a.device());
+	const int H = a.size(-2), W = a.size(-1);
+	const int planes = (int)(a.numel() / ((int64_t)H * W));
+	TORCH_CHECK(d.numel() == 3 * a.numel(), "ssim backward: dmaps do not belong to these images");
+	torch::Tensor up;
+	const float* up_ptr = nullptr;
+	if (upstream.defined() && upstream.numel() != 0) {
+		TORCH_CHECK(upstream.numel() == 1, "ssim backward: upstream gradient must be a scalar");
+		up = image_input(upstream, img, "upstream gradient");
+		up_ptr = up.data_ptr<float>();
+	}
+	torch::Tensor out = torch::empty_like(a);
+	check(rgs_ssim_l1_backward(planes, H, W, a.data_ptr<float>(), b.data_ptr<float>(), d.data_ptr<float>(), (float)w_ssim, (float)w_l1, up_ptr,
+	                           out.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
+	return out.view(img.sizes());
+}
+
+// returns (loss_sum [1] float64, d_normal [3,H,W], d_expected, d_median)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> NormalConsistency(const torch::Tensor& rendered_normal,
+                                                                                           const torch::Tensor& map_expected,
+                                                                                           const torch::Tensor& map_median, const bool from_depth,
+                                                                                           const double inv_fx, const double inv_fy, const double cx,
+                                                                                           const double cy, const double w_expected,
+                                                                                           const double w_median) {
+	torch::Tensor n = image_input(rendered_normal, rendered_normal, "rendered_normal"), e = image_input(map_expected, rendered_normal, "expected map"),
+	              m = image_input(map_median, rendered_normal, "median map");
+	const c10::cuda::CUDAGuard guard(n.device());
+	TORCH_CHECK(n.dim() == 3 && n.size(0) == 3, "rendered_normal must be [3,H,W]");
+	const int H = n.size(1), W = n.size(2);
+	const int64_t want = (from_depth ? 1 : 3) * (int64_t)H * W;
+	TORCH_CHECK(e.numel() == want && m.numel() == want, from_depth ? "depth maps must be [1,H,W]" : "coordinate maps must be [3,H,W]");
+	torch::Tensor loss = torch::empty({1}, n.options().dtype(torch::kFloat64));
+	torch::Tensor dn = torch::empty_like(n), de = torch::empty_like(e), dm = torch::empty_like(m);
+	check(rgs_normal_consistency(H, W, from_depth ? 1 : 0, (float)inv_fx, (float)inv_fy, (float)cx, (float)cy, n.data_ptr<float>(), e.data_ptr<float>(),
+	                             m.data_ptr<float>(), (float)w_expected, (float)w_median, loss.data_ptr<double>(), dn.data_ptr<float>(),
+	                             de.data_ptr<float>(), dm.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
+	return std::make_tuple(loss, dn, de.view(map_expected.sizes()), dm.view(map_median.sizes()));
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -495,6 +561,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("rasterize_gaussians_backward_preprocess", &BackwardPreprocessCUDA);
 	m.def("rasterize_gaussians_split_sh", &RasterizeGaussiansSplitShCUDA);
 	m.def("rasterize_gaussians_backward_split_sh", &RasterizeGaussiansBackwardSplitShCUDA);
+	m.def("ssim_l1_forward", &SsimL1Forward);
+	m.def("ssim_l1_backward", &SsimL1Backward);
+	m.def("normal_consistency", &NormalConsistency);
 	m.def("activate_forward", &ActivateForward);
 	m.def("activate_backward", &ActivateBackward);
 	m.def("densification_stats", &DensificationStats);
