@@ -175,6 +175,14 @@ int32_t rgs_densification_stats(int32_t P, const float* means2D_grad, const int3
                                 float* grad_accum_abs, float* grad_accum_abs_max, float* denom, float* max_radii2D,
                                 void* cuda_stream);
 
+/* rgs_compute_3d_filter: GaussianModel.compute_3D_filter (scene/gaussian_model.py:179-232) as two kernels instead of a Python
+ * loop over cameras.  cams: DEVICE table [n_cams,16] = R (3x3 row-major, Camera.R), T (3), focal_x, focal_y, width, height;
+ * focal_length = max focal_x over the cameras (host).  filter_3D [P] receives distance / focal_length * sqrt(0.2);
+ * max_distance (device scalar) receives the largest distance among points seen by a camera, 0 if none was seen (the
+ * reference raises in that case). */
+int32_t rgs_compute_3d_filter(int32_t P, const float* xyz, int32_t n_cams, const float* cams, float focal_length,
+                              float* filter_3D, float* max_distance, void* cuda_stream);
+
 /* ---- image-side consumers of the maps, opt-in ----
  * rgs_ssim_l1_forward: utils/loss_utils.py:17-18 and :35-63 over `planes` [H,W] fp32 planes.  sums[0] = sum of the SSIM map,
  *   sums[1] = sum |img - gt| (the call zeroes them; divide by planes*H*W for the means).  dmaps ([3,planes,H,W], may be NULL

@@ -107,6 +107,77 @@ __global__ void __launch_bounds__(256) densification_stats_kernel(int P, const f
 	if (max_radii2D != nullptr) max_radii2D[i] = fmaxf(max_radii2D[i], (float)r);  // train.py:187
 }
 
+// ---- 3D smoothing filter (GaussianModel.compute_3D_filter, scene/gaussian_model.py:179-232) ----------------------------------
+// The reference loops over the training cameras in Python, ~15 torch kernels per camera over all P points (a few
+// thousand launches per call at DTU scale).  Here one thread owns a point and walks the camera table (16 floats per
+// camera: R row-major as Camera.R, T, focal_x, focal_y, W, H); the closest valid camera-space depth decides the
+// filter size.  Pass 1 leaves min z (or -1 when no camera sees the point) and the maximum over the seen points;
+// pass 2 gives unseen points that maximum and scales: filter = distance / focal_length * sqrt(0.2).
+constexpr int CAM_FLOATS = 16;
+constexpr int CAM_CHUNK = 256;  // cameras staged in shared memory at a time (16 KiB)
+
+__global__ void __launch_bounds__(256) filter3d_distance_kernel(int P, const float* __restrict__ xyz, int n_cams, const float* __restrict__ cams,
+                                                                 float* __restrict__ distance, unsigned int* __restrict__ max_bits) {
+	__shared__ float s_cam[CAM_CHUNK * CAM_FLOATS];
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = i < P;
+	const float x = live ? xyz[3 * i] : 0.f, y = live ? xyz[3 * i + 1] : 0.f, z = live ? xyz[3 * i + 2] : 0.f;
+	float dist = 100000.0f;
+	bool seen = false;
+	for (int base = 0; base < n_cams; base += CAM_CHUNK) {
+		const int chunk = min(CAM_CHUNK, n_cams - base);
+		__syncthreads();
+		for (int k = threadIdx.x; k < chunk * CAM_FLOATS; k += blockDim.x) s_cam[k] = cams[(size_t)base * CAM_FLOATS + k];
+		__syncthreads();
+		for (int c = 0; c < chunk; c++) {
+			const float* C = s_cam + c * CAM_FLOATS;
+			// xyz @ R + T : one fp32 dot product per column, then the bias
+			const float xc = __fadd_rn(fmaf(z, C[6], fmaf(y, C[3], __fmul_rn(x, C[0]))), C[9]);
+			const float yc = __fadd_rn(fmaf(z, C[7], fmaf(y, C[4], __fmul_rn(x, C[1]))), C[10]);
+			const float zc = __fadd_rn(fmaf(z, C[8], fmaf(y, C[5], __fmul_rn(x, C[2]))), C[11]);
+			const bool valid_depth = zc > 0.2f;
+			const float zz = fmaxf(zc, 0.001f);
+			const float W = C[14], H = C[15];
+			const float px = __fadd_rn(__fmul_rn(__fdiv_rn(xc, zz), C[12]), W * 0.5f);
+			const float py = __fadd_rn(__fmul_rn(__fdiv_rn(yc, zz), C[13]), H * 0.5f);
+			// "similar tangent space filtering as in the paper": 15% margin around the image
+			const bool in_screen = px >= (float)(-0.15 * (double)W) && px <= (float)((double)W * 1.15) && py >= (float)(-0.15 * (double)H) &&
+			                       py <= (float)(1.15 * (double)H);
+			if (valid_depth && in_screen) {
+				dist = fminf(dist, zz);
+				seen = true;
+			}
+		}
+	}
+	const float best = (live && seen) ? dist : -1.0f;
+	if (live) distance[i] = best;
+	// maximum over the seen points (distances are positive: their bit patterns order like unsigned integers)
+	float m = fmaxf(best, 0.0f);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(max_bits, __float_as_uint(m));
+}
+
+__global__ void __launch_bounds__(256) filter3d_finish_kernel(int P, const unsigned int* __restrict__ max_bits, float inv_focal, float scale,
+                                                               float* __restrict__ filter_3D) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	float d = filter_3D[i];
+	if (d < 0.0f) d = __uint_as_float(*max_bits);
+	// torch divides by a Python scalar as a multiplication with its fp32 reciprocal
+	filter_3D[i] = __fmul_rn(__fmul_rn(d, inv_focal), scale);
+}
+
+void launch_compute_3d_filter(int P, const float* xyz, int n_cams, const float* cams, float focal_length, float* filter_3D, float* max_distance,
+                              cudaStream_t s) {
+	unsigned int* max_bits = reinterpret_cast<unsigned int*>(max_distance);
+	cudaMemsetAsync(max_bits, 0, sizeof(unsigned int), s);
+	filter3d_distance_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, xyz, n_cams, cams, filter_3D, max_bits);
+	count_launch();
+	filter3d_finish_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, max_bits, 1.0f / focal_length, (float)0.4472135954999579 /* 0.2 ** 0.5 */, filter_3D);
+	count_launch();
+}
+
 void launch_activate_forward(int P, const float* raw_scaling, const float* raw_opacity, const float* raw_rotation, const float* filter_3D, float* scales,
                              float* opacity, float* rotations, cudaStream_t s) {
 	activate_forward_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, raw_scaling, raw_opacity, raw_rotation, filter_3D, scales, opacity, rotations);

@@ -370,6 +370,16 @@ static int32_t after_launch() {
 	return e == cudaSuccess ? (int32_t)RGS_OK : fail(RGS_E_CUDA, cudaGetErrorString(e));
 }
 
+int32_t rgs_compute_3d_filter(int32_t P, const float* xyz, int32_t n_cams, const float* cams, float focal_length, float* filter_3D,
+                              float* max_distance, void* cuda_stream) {
+	if (P < 0 || n_cams < 0) return fail(RGS_E_INVALID, "negative count");
+	if (P == 0) return RGS_OK;
+	if (!xyz || !filter_3D || !max_distance || (n_cams > 0 && !cams)) return fail(RGS_E_INVALID, "null pointer");
+	if (!(focal_length > 0.0f)) return fail(RGS_E_INVALID, "focal_length must be positive");
+	launch_compute_3d_filter(P, xyz, n_cams, cams, focal_length, filter_3D, max_distance, (cudaStream_t)cuda_stream);
+	return after_launch();
+}
+
 int32_t rgs_ssim_l1_forward(int32_t planes, int32_t H, int32_t W, const float* img, const float* gt, float* dmaps, double* sums, void* cuda_stream) {
 	if (planes < 0 || H <= 0 || W <= 0) return fail(RGS_E_INVALID, "image size must be positive");
 	if (!img || !gt || !sums) return fail(RGS_E_INVALID, "null pointer");

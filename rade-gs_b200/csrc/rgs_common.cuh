@@ -246,6 +246,9 @@ void launch_activate_backward(int P, const float* raw_scaling, const float* raw_
 void launch_densification_stats(int P, const float* means2D_grad, const int* radii, float* grad_accum, float* grad_accum_abs, float* grad_accum_abs_max,
                                 float* denom, float* max_radii2D, cudaStream_t s);
 
+void launch_compute_3d_filter(int P, const float* xyz, int n_cams, const float* cams, float focal_length, float* filter_3D, float* max_distance,
+                              cudaStream_t s);
+
 // fused image-side losses (rgs_image_loss.cu)
 void launch_ssim_l1_forward(int planes, int H, int W, const float* img, const float* gt, float* dmaps, double* sums, cudaStream_t s);
 void launch_ssim_l1_backward(int planes, int H, int W, const float* img, const float* gt, const float* dmaps, float w_ssim, float w_l1,

@@ -482,6 +482,21 @@ void DensificationStats(const torch::Tensor& means2D_grad, const torch::Tensor& 
 	                              grad_accum_abs_max.data_ptr<float>(), denom.data_ptr<float>(), mr, at::cuda::getCurrentCUDAStream().stream()));
 }
 
+// returns (filter_3D [P,1], max_distance [1])
+std::tuple<torch::Tensor, torch::Tensor> Compute3DFilter(const torch::Tensor& xyz, const torch::Tensor& cams, const double focal_length) {
+	TORCH_CHECK(xyz.is_cuda(), "xyz must be a CUDA tensor: no CPU path");
+	const c10::cuda::CUDAGuard guard(xyz.device());
+	torch::Tensor x = as_input(xyz, xyz, "xyz"), c = as_input(cams, xyz, "camera table");
+	const int P = xyz.size(0);
+	TORCH_CHECK(c.numel() % 16 == 0, "camera table must be [n_cams,16]");
+	const int n = (int)(c.numel() / 16);
+	torch::Tensor out = torch::empty({P, 1}, x.options()), mx = torch::zeros({1}, x.options());
+	if (P)
+		check(rgs_compute_3d_filter(P, x.data_ptr<float>(), n, n ? c.data_ptr<float>() : nullptr, (float)focal_length, out.data_ptr<float>(),
+		                            mx.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
+	return std::make_tuple(out, mx);
+}
+
 // ---- fused image-side losses (opt-in) -----------------------------------------------------------------
 
 torch::Tensor image_input(const torch::Tensor& t, const torch::Tensor& like, const char* name) {
@@ -561,6 +576,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("rasterize_gaussians_backward_preprocess", &BackwardPreprocessCUDA);
 	m.def("rasterize_gaussians_split_sh", &RasterizeGaussiansSplitShCUDA);
 	m.def("rasterize_gaussians_backward_split_sh", &RasterizeGaussiansBackwardSplitShCUDA);
+	m.def("compute_3d_filter", &Compute3DFilter);
 	m.def("ssim_l1_forward", &SsimL1Forward);
 	m.def("ssim_l1_backward", &SsimL1Backward);
 	m.def("normal_consistency", &NormalConsistency);

@@ -49,3 +49,33 @@ def add_densification_stats_(means2D_grad: torch.Tensor, radii: torch.Tensor, xy
     empty = torch.empty(0, device=means2D_grad.device)
     _C.densification_stats(means2D_grad, radii, xyz_gradient_accum, xyz_gradient_accum_abs, xyz_gradient_accum_abs_max, denom,
                            empty if max_radii2D is None else max_radii2D)
+
+
+@torch.no_grad()
+def compute_3D_filter(xyz: torch.Tensor, cameras) -> torch.Tensor:
+    """``GaussianModel.compute_3D_filter`` (scene/gaussian_model.py:179-232): returns ``filter_3D`` [P,1].
+
+    ``cameras`` is the iterable the reference passes (objects with ``R``, ``T``, ``FoVx``, ``FoVy``, ``image_width``,
+    ``image_height``).  One kernel walks all cameras per point instead of ~15 torch kernels per camera (the camera
+    table streams through shared memory 256 cameras at a time).
+    """
+    import math
+
+    import numpy as np
+
+    rows, focal_length = [], 0.0
+    for cam in cameras:
+        W, H = cam.image_width, cam.image_height
+        focal_x = W / (2 * math.tan(cam.FoVx / 2.))
+        focal_y = H / (2 * math.tan(cam.FoVy / 2.))
+        R = np.asarray(cam.R, dtype=np.float32).reshape(9)
+        T = np.asarray(cam.T, dtype=np.float32).reshape(3)
+        rows.append(np.concatenate([R, T, np.asarray([focal_x, focal_y, W, H], dtype=np.float32)]))
+        focal_length = max(focal_length, focal_x)
+    if not rows:
+        raise ValueError("compute_3D_filter needs at least one camera")
+    table = torch.from_numpy(np.stack(rows)).to(xyz.device)
+    out, mx = _C.compute_3d_filter(xyz, table, focal_length)
+    if float(mx) == 0.0:  # the reference fails in distance[valid_points].max() on an empty selection
+        raise RuntimeError("compute_3D_filter: no point is seen by any camera")
+    return out

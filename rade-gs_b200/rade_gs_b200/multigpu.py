@@ -115,6 +115,19 @@ class _ShardedRasterize(torch.autograd.Function):
         return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, None, None, None
 
 
+class _GatherSlabs(torch.autograd.Function):
+    """all-reduce(sum) of slab-filled maps forward; identity backward (every rank holds the same full-image loss)."""
+
+    @staticmethod
+    def forward(ctx, img, group):
+        out = img.detach().clone()
+        return allreduce_sum_(out, group)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return grad_out, None
+
+
 class ShardedGaussianRasterizer(torch.nn.Module):
     """`GaussianRasterizer` whose work is split by tile rows over the ranks of a process group.
 
@@ -151,6 +164,10 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         return min(self.slab[0] * TILE, H), min(self.slab[1] * TILE, H)
 
     def gather_image(self, img: torch.Tensor) -> torch.Tensor:
-        """Sum of the slab images = the whole image (rows outside a rank's slab are zero)."""
-        out = img.clone()
-        return allreduce_sum_(out, self.group)
+        """Sum of the slab images = the whole image (rows outside a rank's slab are zero).
+
+        Differentiable: with the whole image on every rank an unchanged full-image loss (train.py:130-165: L1, SSIM,
+        normal consistency) can be evaluated redundantly per rank; its gradient flows back unchanged and the sharded
+        rasterizer's backward reads only the rows of its own slab, so nothing is counted twice.
+        """
+        return _GatherSlabs.apply(img, self.group)

@@ -84,3 +84,42 @@ def test_allreduce_is_noop_without_process_group():
     from rade_gs_b200.multigpu import allreduce_sum_
     t = torch.arange(6.0)
     assert torch.equal(allreduce_sum_(t.clone()), t)
+
+
+def _gather_worker(rank, world, port, tmpdir):
+    sys.path.insert(0, os.path.join(ROOT, "rade-gs_b200"))
+    from rade_gs_b200 import multigpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, W = 40, 24  # 3 tile rows -> slabs of 2 and 1 rows
+        g = torch.Generator().manual_seed(3)
+        whole = torch.rand(3, H, W, generator=g)
+        weight = torch.rand(3, H, W, generator=g)
+        slabs = multigpu.partition_tile_rows(multigpu.tile_rows(H), world)
+        r0, r1 = min(slabs[rank][0] * 16, H), min(slabs[rank][1] * 16, H)
+        mine = torch.zeros_like(whole)
+        mine[:, r0:r1] = whole[:, r0:r1]
+        mine.requires_grad_(True)
+        full = multigpu._GatherSlabs.apply(mine, None)
+        loss = (full * full * weight).sum()  # any full-image loss, evaluated redundantly on each rank
+        loss.backward()
+        torch.save({"full": full.detach(), "grad": mine.grad, "rows": (r0, r1), "whole": whole, "weight": weight},
+                   os.path.join(tmpdir, f"gather{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_image_is_differentiable_across_two_ranks(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    covered = 0
+    for rank in range(2):
+        d = torch.load(tmp_path / f"gather{rank}.pt")
+        assert torch.equal(d["full"], d["whole"])  # slabs are disjoint: the sum reassembles the image exactly
+        r0, r1 = d["rows"]
+        want = 2 * d["whole"] * d["weight"]
+        assert torch.allclose(d["grad"][:, r0:r1], want[:, r0:r1])  # the rows this rank's backward consumes
+        covered += r1 - r0
+    assert covered == 40
