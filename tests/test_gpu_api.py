@@ -46,7 +46,7 @@ def test_autograd_module_matches_golden(case):
     for name, t in (("means3D", leaves["means3D"]), ("means2D", means2D), ("sh", leaves["shs"]), ("opacity", leaves["opacities"]),
                     ("scales", leaves["scales"]), ("rotations", leaves["rotations"])):
         noise = float(d["grad_noise_" + name]) / (np.abs(d["grad_" + name]).max() + 1e-30)
-        grad_close_gpu(t.grad.cpu().numpy(), d["grad_" + name], name, rel=1e-3 + 2 * noise, elem=1e-3 + 2 * noise)
+        grad_close_gpu(t.grad.cpu().numpy(), d["grad_" + name], name, rel=1e-3 + 4 * noise, elem=1e-3 + 4 * noise)
     # densification statistics consumer (scene/gaussian_model.py:743-747) reads these two slices
     assert means2D.grad.shape == (sc.means3D.shape[0], 3) and bool((means2D.grad[:, 2] >= 0).all())
 
