@@ -13,6 +13,8 @@
  *   orc_render_backward      backward.cu:631-1016  (scatter sums in double, one thread, deterministic)
  *   orc_preprocess_backward  backward.cu:145-488, :560-628, :21-140, :492-555
  *                            including the dL_dconic-for-conic_opacity aliasing (rasterizer_impl.cu:569)
+ *   orc_inte_geometry        forward.cu:187-235 (computeCov2D<INTE>: inverse ray-space covariance, well-conditioned flag)
+ *   orc_integrate            forward.cu:857-900 (points), rasterizer_impl.cu:114-145 (point -> tile), forward.cu:938-1372
  *
  * Parity pin: tests/test_oracle_golden.py checks every function against tests/golden/<case>.npz, which were
  * produced by the unmodified reference CUDA build on a B200 (tools/gen_golden.py).
@@ -823,4 +825,180 @@ void orc_preprocess_backward(const orc_scene* s, const orc_geom* g, const orc_sg
 #undef Dm
 		}
 	}
+}
+
+/* ---- integrate_gaussians_to_points ---------------------------------------------------------
+ * computeCov2D<INTE> extras, forward.cu:187-235: the inverse covariance in (pixel x, pixel y, ray depth) space.  The
+ * reference leaves it unassigned for ill-conditioned covariances (its else-branch fills a shadowed local, :214); those
+ * Gaussians get condition = 0 and zeros here.  invraycov [P,6] must arrive zero-filled (rasterize_points.cu:317). */
+void orc_inte_geometry(const orc_scene* s, const orc_geom* g, float* invraycov, uint8_t* condition) {
+	const float focal_y = s->H / (2.0f * s->tan_fovy), focal_x = s->W / (2.0f * s->tan_fovx);
+	const float* V = s->viewmatrix;
+	for (int idx = 0; idx < s->P; idx++) {
+		float pv[3]; xf4x3(s->means3D + 3 * idx, V, pv);
+		if (pv[2] <= 0.2f) continue;
+		const float* cov6 = g->cov3D + 6 * idx;
+		float t[3] = {pv[0], pv[1], pv[2]};
+		const float limx = 1.3f * s->tan_fovx, limy = 1.3f * s->tan_fovy;
+		float txtz = t[0] / t[2], tytz = t[1] / t[2];
+		t[0] = fminf2(limx, fmaxf2(-limx, txtz)) * t[2];
+		t[1] = fminf2(limy, fmaxf2(-limy, tytz)) * t[2];
+		txtz = t[0] / t[2]; tytz = t[1] / t[2];
+		m3 Wm = m3_make(V[0], V[4], V[8], V[1], V[5], V[9], V[2], V[6], V[10]);
+		sig_inv si = sigma_inverse(cov6);
+		condition[idx] = (uint8_t)si.well;
+		m3 cci = m3_mul(m3_mul(m3_t(Wm), si.inv), Wm);
+		v3 uvh = v3_make(txtz, tytz, 1), uvh_mn = v3_normalize(m3_mulv(cci, uvh));
+		if (isnan(uvh_mn.v[0]) || !si.solved || !si.well) continue;
+		const float u2 = txtz * txtz, v2 = tytz * tytz, uv = txtz * tytz;
+		const float l = sqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+		const float ltz = u2 + v2 + 1;
+		m3 full = m3_scale(m3_make(v2 + 1, -uv, txtz / l * ltz, -uv, u2 + 1, tytz / l * ltz, -txtz, -tytz, 1 / l * ltz), t[2] / (u2 + v2 + 1));
+		m3 T2 = m3_mul(Wm, m3_t(full));
+		m3 inv = m3_mul(m3_mul(m3_t(T2), si.inv), T2);
+		m3 sc = m3_make(1 / focal_x, 0, 0, 0, 1 / focal_y, 0, 0, 0, 1);
+		inv = m3_mul(m3_mul(sc, inv), sc);
+		float* o = invraycov + 6 * idx;
+		o[0] = inv.c[0][0]; o[1] = inv.c[0][1]; o[2] = inv.c[0][2]; o[3] = inv.c[1][1]; o[4] = inv.c[1][2]; o[5] = inv.c[2][2];
+	}
+}
+
+#define ORC_MAX_CONTRIB (512 * 4)   /* MAX_NUM_CONTRIBUTORS * 4, auxiliary.h:31, forward.cu:1126 */
+
+typedef struct {
+	float* out_color;          /* [9,H,W], zero-filled by the caller */
+	float* alpha_integrated;   /* [PN]  filled with 1      (rasterize_points.cu:313) */
+	float* color_integrated;   /* [PN,3] filled with 0 */
+	float* coordinate2d;       /* [PN,2] filled with 0 */
+	float* sdf;                /* [PN]  filled with -1000 */
+} orc_integrate_out;
+
+/* forward.cu:938-1372 per pixel, serially.  Phase 1 renders with five sample positions (centre + corners) and records which
+ * list entries contributed at any of them; phase 2 re-walks exactly those entries for every query point that projects
+ * into the pixel, with the 3D (ray-space) Gaussian instead of the 2D conic.  Returns the number of pixels that hit the
+ * contributor cap (the reference prints an error and stops that pixel). */
+int orc_integrate(int W, int H, float tan_fovx, float tan_fovy, const float* bg, const uint32_t* ranges, const uint32_t* point_list,
+                  const orc_geom* g, const float* invraycov, const uint8_t* condition, int PN, const float* points3D, const float* viewmatrix,
+                  orc_integrate_out* o) {
+	const int gx = (W + TILE - 1) / TILE;
+	const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);
+	const size_t HW = (size_t)H * W;
+	/* preprocessPointsCUDA (forward.cu:857-900): bucket the points by the pixel they fall into */
+	float* pxy = (float*)malloc((size_t)PN * 2 * sizeof(float));
+	float* pdepth = (float*)malloc((size_t)PN * sizeof(float));
+	int* ppix = (int*)malloc((size_t)PN * sizeof(int));
+	int* head = (int*)malloc((HW + 1) * sizeof(int));
+	int* order = (int*)malloc((size_t)(PN > 0 ? PN : 1) * sizeof(int));
+	memset(head, 0, (HW + 1) * sizeof(int));
+	for (int i = 0; i < PN; i++) {
+		ppix[i] = -1;
+		float pv[3]; xf4x3(points3D + 3 * i, viewmatrix, pv);
+		if (pv[2] <= 0.2f) continue;
+		const float ix = (float)((double)(focal_x * pv[0] / (pv[2] + 0.0000001f)) + W / 2.);
+		const float iy = (float)((double)(focal_y * pv[1] / (pv[2] + 0.0000001f)) + H / 2.);
+		if (ix < 0 || ix >= W || iy < 0 || iy >= H) continue;
+		pdepth[i] = sqrtf(pv[0] * pv[0] + pv[1] * pv[1] + pv[2] * pv[2]);
+		pxy[2 * i] = ix; pxy[2 * i + 1] = iy;
+		/* the pixel whose half-open box [x, x+1) x [y, y+1) holds the point (forward.cu:1212-1213) */
+		ppix[i] = (int)iy * W + (int)ix;
+		head[ppix[i] + 1]++;
+	}
+	for (size_t p = 0; p < HW; p++) head[p + 1] += head[p];
+	{
+		int* fill = (int*)malloc((HW + 1) * sizeof(int));
+		memcpy(fill, head, (HW + 1) * sizeof(int));
+		for (int i = 0; i < PN; i++) if (ppix[i] >= 0) order[fill[ppix[i]]++] = i;
+		free(fill);
+	}
+	static const float off_x[5] = {0.0f, -0.5f, 0.5f, -0.5f, 0.5f}, off_y[5] = {0.0f, -0.5f, -0.5f, 0.5f, 0.5f};
+	uint32_t* contributed = (uint32_t*)malloc(ORC_MAX_CONTRIB * sizeof(uint32_t));
+	int overflowed = 0;
+	for (int py = 0; py < H; py++) for (int px = 0; px < W; px++) {
+		const size_t pix = (size_t)W * py + px;
+		const float pxf = (float)px + 0.5f, pyf = (float)py + 0.5f;
+		const uint32_t* rg = ranges + 2 * ((py / TILE) * gx + px / TILE);
+		float T = 1.0f, C[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		float mid_depth_center = 0, mid_plane[2] = {0, 0}, mid_mean2d[2] = {0, 0};
+		float corner_T[5] = {1, 1, 1, 1, 1};
+		uint32_t contributor = 0, last = 0; int n_contrib = 0;
+		for (uint32_t it = rg[0]; it < rg[1]; it++) {
+			contributor++;
+			const int id = (int)point_list[it];
+			const float* co = g->conic_opacity + 4 * id;
+			const float depth_center = g->ts[id];
+			const float plx = g->ray_planes[2 * id], ply = g->ray_planes[2 * id + 1];
+			const float mx = g->means2D[2 * id], my = g->means2D[2 * id + 1];
+			int used = 0;
+			for (int k = 0; k < 5; k++) {
+				const float dx = mx - pxf - off_x[k], dy = my - pyf - off_y[k];
+				const float depth = depth_center + (plx * dx + ply * dy);
+				const float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+				if (power > 0.0f) continue;
+				const float alpha = fminf2(0.99f, co[3] * expf(power));
+				if (alpha < 1.0f / 255.0f) continue;
+				const float test_T = corner_T[k] * (1 - alpha);
+				if (test_T < 0.0001f) continue;
+				if (k == 0) for (int ch = 0; ch < 3; ch++) C[ch] += g->rgb[3 * id + ch] * alpha * T;
+				if (depth > C[6]) C[6] = depth;
+				if (k == 0) {
+					C[7] += alpha * T;
+					C[3] += depth * alpha * T;
+					if (T > 0.5) { C[4] = depth; mid_depth_center = depth_center; mid_plane[0] = plx; mid_plane[1] = ply; mid_mean2d[0] = mx; mid_mean2d[1] = my; }
+					T = test_T;
+				}
+				corner_T[k] = test_T;
+				used = 1;
+			}
+			if (used) {
+				last = contributor;
+				contributed[n_contrib++] = contributor;
+				if (n_contrib >= ORC_MAX_CONTRIB) { overflowed++; break; }
+			}
+		}
+		for (int ch = 0; ch < 3; ch++) o->out_color[ch * HW + pix] = C[ch] + T * bg[ch];
+		o->out_color[3 * HW + pix] = C[3];
+		o->out_color[4 * HW + pix] = C[4];
+		o->out_color[6 * HW + pix] = C[6];
+		o->out_color[7 * HW + pix] = C[7];
+		o->out_color[8 * HW + pix] = (float)(head[pix + 1] - head[pix]);
+		(void)last;
+		for (int q = head[pix]; q < head[pix + 1]; q++) {
+			const int pid = order[q];
+			const float qx = pxy[2 * pid], qy = pxy[2 * pid + 1], qdepth = pdepth[pid];
+			float pa = 0.f, pT = 1.f;
+			for (int c = 0; c < n_contrib; c++) {
+				const int id = (int)point_list[rg[0] + contributed[c] - 1];
+				const float* co = g->conic_opacity + 4 * id;
+				const float depth_center = g->ts[id];
+				const float dx = g->means2D[2 * id] - qx, dy = g->means2D[2 * id + 1] - qy;
+				const float depth = depth_center + (g->ray_planes[2 * id] * dx + g->ray_planes[2 * id + 1] * dy);
+				const float* ic = invraycov + 6 * id;
+				float alpha;
+				float dz;
+				if (condition[id]) dz = depth_center - fminf2(qdepth, depth);
+				else if (qdepth < depth) { continue; /* alpha = 0 */ }
+				else dz = depth_center;
+				{
+					/* glm::dot(delta, M * delta), M symmetric from the six stored entries (forward.cu:1300-1312) */
+					const float m0 = ic[0] * dx + ic[1] * dy + ic[2] * dz;
+					const float m1 = ic[1] * dx + ic[3] * dy + ic[4] * dz;
+					const float m2 = ic[2] * dx + ic[4] * dy + ic[5] * dz;
+					const float power = -0.5f * (dx * m0 + dy * m1 + dz * m2);
+					alpha = fminf2(0.99f, co[3] * expf(power));
+				}
+				if (alpha < 1.0f / 255.0f) continue;
+				pa += alpha * pT;
+				pT = pT * (1 - alpha);
+			}
+			o->alpha_integrated[pid] = pa;
+			for (int ch = 0; ch < 3; ch++) o->color_integrated[3 * pid + ch] = C[ch] + T * bg[ch];
+			o->coordinate2d[2 * pid] = qx; o->coordinate2d[2 * pid + 1] = qy;
+			if (qdepth > 0) {
+				const float dx = mid_mean2d[0] - qx, dy = mid_mean2d[1] - qy;
+				o->sdf[pid] = (mid_depth_center + (mid_plane[0] * dx + mid_plane[1] * dy)) - qdepth;
+			}
+		}
+	}
+	free(contributed); free(order); free(head); free(ppix); free(pdepth); free(pxy);
+	return overflowed;
 }

@@ -219,6 +219,36 @@ def backward(inp: Inputs, fwd: dict, grads: dict, fix_mip_gradient: bool = False
     return out
 
 
+class _IntegrateOut(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("out_color", "alpha_integrated", "color_integrated", "coordinate2d", "sdf")]
+
+
+def integrate(inp: Inputs, points3D) -> dict:
+    """`integrate_gaussians_to_points` (rasterize_points.cu:269-388): the reference always runs it with kernel_size 0 and both
+    geometry variants on; `inp` must have been built with kernel_size=0."""
+    assert inp.kernel_size == 0.0, "GaussianRasterizer.integrate passes kernel_size 0.0 (diff_gaussian_rasterization/__init__.py:281)"
+    points3D = np.ascontiguousarray(points3D, np.float32)
+    PN, P, H, W = points3D.shape[0], inp.P, inp.H, inp.W
+    g = preprocess(inp)
+    b = binning(W, H, g["radii"], g["means2D"], g["depths"], g["tiles_touched"])
+    invraycov = np.zeros((P, 6), np.float32)
+    condition = np.zeros(P, np.uint8)
+    sc, cg = inp.c_scene(), _c_geom(g)
+    lib().orc_inte_geometry(C.byref(sc), C.byref(cg), _p(invraycov, _f32p), _p(condition, _u8p))
+    out = dict(color=np.zeros((9, H, W), np.float32), alpha_integrated=np.ones(PN, np.float32), color_integrated=np.zeros((PN, 3), np.float32),
+               point_coordinate=np.zeros((PN, 2), np.float32), point_sdf=np.full(PN, -1000.0, np.float32))
+    co = _IntegrateOut(_p(out["color"], _f32p), _p(out["alpha_integrated"], _f32p), _p(out["color_integrated"], _f32p),
+                       _p(out["point_coordinate"], _f32p), _p(out["point_sdf"], _f32p))
+    ranges = np.ascontiguousarray(b["ranges"], np.uint32)
+    pl = np.ascontiguousarray(b["point_list"], np.uint32)
+    lib().orc_integrate.restype = C.c_int
+    over = lib().orc_integrate(C.c_int(W), C.c_int(H), C.c_float(inp.tanfovx), C.c_float(inp.tanfovy), _p(inp.bg, _f32p), _p(ranges, _u32p),
+                               _p(pl, _u32p), C.byref(cg), _p(invraycov, _f32p), _p(condition, _u8p), C.c_int(PN), _p(points3D, _f32p),
+                               _p(inp.viewmatrix, _f32p), C.byref(co))
+    out.update(radii=g["radii"], num_rendered=b["num_rendered"], invraycov=invraycov, condition=condition, overflowed=int(over), geom=g, binning=b)
+    return out
+
+
 def eig_sym3(cov6):
     cov6 = np.ascontiguousarray(cov6, np.float32)
     lam = np.zeros(3, np.float32)

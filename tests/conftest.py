@@ -11,7 +11,9 @@ for p in (os.path.join(ROOT, "rade-gs_b200"), os.path.join(ROOT, "oracle"), ROOT
         sys.path.insert(0, p)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz")) if os.path.isdir(GOLDEN_DIR) else []
+_ALL_GOLDEN = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz")) if os.path.isdir(GOLDEN_DIR) else []
+GOLDEN_CASES = [c for c in _ALL_GOLDEN if not c.startswith("integrate_")]       # rasterize fwd/bwd (tools/gen_golden.py)
+INTEGRATE_CASES = [c for c in _ALL_GOLDEN if c.startswith("integrate_")]        # integrate (tools/gen_golden_integrate.py)
 
 
 def pytest_configure(config):
@@ -37,6 +39,16 @@ def golden_oracle_inputs(d):
     return oracle.Inputs(d["in_means3D"], d["in_opacities"], d["in_viewmatrix"], d["in_projmatrix"], d["in_campos"], d["in_bg"],
                          int(d["meta_W"]), int(d["meta_H"]), float(d["in_tanfov"][0]), float(d["in_tanfov"][1]), sh_degree=int(d["meta_deg"]),
                          kernel_size=float(d["meta_ks"]), require_coord=bool(d["meta_coord"]), require_depth=bool(d["meta_depth"]), **kw)
+
+
+def integrate_oracle_inputs(d):
+    """oracle.Inputs for an integrate fixture: kernel_size 0, SH truncated to the fixture's degree (as the generator passed it)."""
+    import oracle
+    M = (int(d["meta_deg"]) + 1) ** 2
+    return oracle.Inputs(d["in_means3D"], d["in_opacities"], d["in_viewmatrix"], d["in_projmatrix"], d["in_campos"], d["in_bg"],
+                         int(d["meta_W"]), int(d["meta_H"]), float(d["in_tanfov"][0]), float(d["in_tanfov"][1]), sh_degree=int(d["meta_deg"]),
+                         kernel_size=0.0, require_coord=True, require_depth=True, shs=np.ascontiguousarray(d["in_shs"][:, :M]),
+                         scales=d["in_scales"], rotations=d["in_rotations"])
 
 
 def golden_upstream(d):
