@@ -105,6 +105,28 @@ typedef struct rgs_buffers {
 int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* g, const rgs_forward_out* out,
                     const rgs_buffers* bufs, void* cuda_stream);
 
+/* ---- opacity integration at query points ----
+ * Replaces CudaRasterizer::Rasterizer::integrate (rasterizer.h:68-108, rasterizer_impl.cu:573-844; binding
+ * rasterize_points.cu:269-388).  All outputs are fully written by the call (untouched points get the reference's fill values
+ * 1 / 0 / 0 / -1000; out_color channel 5 is zero, channel 8 counts the points per pixel).  cam->kernel_size is used as
+ * given (the reference's Python wrapper passes 0.0); require_coord / require_depth / tile rows are ignored. */
+typedef struct rgs_integrate_io {
+	int32_t PN;
+	const float* points3D;        /* [PN,3] query points (world space)                         */
+	float* out_color;             /* [9,H,W] rgb, expected depth, median depth, 0, max depth, alpha, points per pixel */
+	float* out_alpha_integrated;  /* [PN]                                                      */
+	float* out_color_integrated;  /* [PN,3]                                                    */
+	float* out_coordinate2d;      /* [PN,2] pixel coordinates of the projected points          */
+	float* out_sdf;               /* [PN]   median-splat depth along the ray minus point depth */
+	int32_t* radii;               /* [P]                                                       */
+} rgs_integrate_io;
+
+/* Returns num_rendered or a negative rgs_status.  point_buffer is a fourth resizable scratch buffer (the reference's
+ * pointBuffer / point_binningBuffer).  overflowed_pixels (may be NULL; non-NULL costs one more stream synchronisation)
+ * receives the number of pixels that collected 2048 contributing splats and stopped there, as in the reference. */
+int64_t rgs_integrate(const rgs_camera* cam, const rgs_gaussians* g, const rgs_integrate_io* io, const rgs_buffers* bufs,
+                      rgs_resize_fn point_buffer, void* point_buffer_user, int32_t* overflowed_pixels, void* cuda_stream);
+
 /* Upstream gradients of the seven maps (rasterize_points.h:57-63) + forward results read by backward. */
 typedef struct rgs_backward_in {
 	const float* dL_dout_color;  /* [3,H,W] */

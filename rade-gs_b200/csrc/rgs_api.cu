@@ -194,12 +194,11 @@ int32_t rgs_stage_times(const char** names, double* total_ms, int64_t* launches,
 }
 int32_t rgs_grad_stride(int32_t require_coord, int32_t /*require_depth*/) { return grad_floats(require_coord != 0); }
 
-int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_forward_out* out, const rgs_buffers* bufs, void* cuda_stream) {
-	FwdParams p;
-	int rc = make_params(cam, gs, p);
-	if (rc != RGS_OK) return rc;
-	if (!out || !bufs || !bufs->geom || !bufs->binning || !bufs->image) return fail(RGS_E_INVALID, "null outputs / buffer callbacks");
-	cudaStream_t s = (cudaStream_t)cuda_stream;
+// preprocess -> tile counts -> (one host sync for the instance count) -> binning / sort: everything before blending.
+// Shared by rgs_forward and rgs_integrate.  Returns num_rendered or a negative status.
+static int64_t forward_to_binning(const rgs_camera* cam, const FwdParams& p, int* radii, const rgs_buffers* bufs, cudaStream_t s, GeomView& g,
+                                  BinView& b, ImgView& img) {
+	int rc;
 	const int P = p.P;
 	const size_t N = (size_t)p.W * p.H;
 	const int tiles = p.grid_x * p.grid_y;
@@ -209,21 +208,20 @@ int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_fo
 	carve_img(nullptr, tiles, N, p.coord, p.depth, &img_bytes);
 	char* img_ptr = bufs->image(bufs->image_user, img_bytes);
 	if (!img_ptr) return fail(RGS_E_ALLOC, "image buffer callback returned NULL");
-	ImgView img = carve_img(img_ptr, tiles, N, p.coord, p.depth, nullptr);
-	RenderOut ro{out->out_color, out->out_coord, out->out_mcoord, out->out_alpha, out->out_normal, out->out_depth, out->out_mdepth};
+	img = carve_img(img_ptr, tiles, N, p.coord, p.depth, nullptr);
 
 	const size_t scan_bytes = P > 0 ? scan_temp_bytes(P) : 0;
 	size_t geom_bytes = 0;
 	carve_geom(nullptr, P, p.coord, scan_bytes, &geom_bytes);
 	char* geom_ptr = bufs->geom(bufs->geom_user, geom_bytes);
 	if (!geom_ptr) return fail(RGS_E_ALLOC, "geometry buffer callback returned NULL");
-	GeomView g = carve_geom(geom_ptr, P, p.coord, scan_bytes, nullptr);
+	g = carve_geom(geom_ptr, P, p.coord, scan_bytes, nullptr);
 
 	int64_t R = 0;
 	uint32_t max_list = 0;
 	if (P > 0) {
 		RGS_CUDA_TRY(cudaMemsetAsync(img.tile_count, 0, (size_t)tiles * sizeof(uint32_t), s));
-		{ StageScope sc(ST_PREPROCESS, s); launch_preprocess_forward(p, g, out->radii, img.tile_count, s); }
+		{ StageScope sc(ST_PREPROCESS, s); launch_preprocess_forward(p, g, radii, img.tile_count, s); }
 		if ((rc = debug_sync(cam, s, "preprocess")) != RGS_OK) return rc;
 		{ StageScope sc(ST_SCAN, s); launch_tile_scan(p, img, s); }
 		// the one host sync of the forward pass: the instance count sizes the binning buffers and is returned to the
@@ -242,22 +240,100 @@ int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_fo
 	carve_bin(nullptr, (size_t)R, tiles, sort_bytes, &bin_bytes);
 	char* bin_ptr = bufs->binning(bufs->binning_user, bin_bytes);
 	if (!bin_ptr) return fail(RGS_E_ALLOC, "binning buffer callback returned NULL");
-	BinView b = carve_bin(bin_ptr, (size_t)R, tiles, sort_bytes, nullptr);
+	b = carve_bin(bin_ptr, (size_t)R, tiles, sort_bytes, nullptr);
 
 	if (P == 0) {
 		RGS_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, (size_t)tiles * sizeof(uint2), s));
 	} else if (tile_path) {
 		StageScope sc(ST_BINNING, s);
-		launch_tile_binning(p, g, b, img, out->radii, R, max_list, s);
+		launch_tile_binning(p, g, b, img, radii, R, max_list, s);
 	} else {
 		// a tile list too long for the shared-memory sort: global radix path (Gaussian-major offsets + 45-bit sort)
 		StageScope sc(ST_BINNING, s);
 		launch_scan(g, P, s);
-		launch_binning(p, g, b, img, out->radii, R, s);
+		launch_binning(p, g, b, img, radii, R, s);
 	}
 	if ((rc = debug_sync(cam, s, "binning")) != RGS_OK) return rc;
+	return R;
+}
+
+int64_t rgs_forward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_forward_out* out, const rgs_buffers* bufs, void* cuda_stream) {
+	FwdParams p;
+	int rc = make_params(cam, gs, p);
+	if (rc != RGS_OK) return rc;
+	if (!out || !bufs || !bufs->geom || !bufs->binning || !bufs->image) return fail(RGS_E_INVALID, "null outputs / buffer callbacks");
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	GeomView g;
+	BinView b;
+	ImgView img;
+	const int64_t R = forward_to_binning(cam, p, out->radii, bufs, s, g, b, img);
+	if (R < 0) return R;
+	RenderOut ro{out->out_color, out->out_coord, out->out_mcoord, out->out_alpha, out->out_normal, out->out_depth, out->out_mdepth};
 	{ StageScope sc(ST_RENDER_FWD, s); launch_render_forward(p, g, b, img, ro, s); }
 	if ((rc = debug_sync(cam, s, "render")) != RGS_OK) return rc;
+	return R;
+}
+
+// Replaces CudaRasterizer::Rasterizer::integrate (rasterizer.h:68-108, rasterizer_impl.cu:573-844).
+int64_t rgs_integrate(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_integrate_io* io, const rgs_buffers* bufs, rgs_resize_fn point_buffer,
+                      void* point_buffer_user, int32_t* overflowed_pixels, void* cuda_stream) {
+	if (!cam) return fail(RGS_E_INVALID, "null camera / gaussians");
+	rgs_camera c = *cam;
+	c.require_depth = 1;  // the integrate path always carries the ray-space planes (rasterizer_impl.cu:634-668)
+	c.require_coord = 0;
+	c.tile_row_begin = 0;
+	c.tile_row_end = -1;
+	FwdParams p;
+	int rc = make_params(&c, gs, p);
+	if (rc != RGS_OK) return rc;
+	if (!io || !bufs || !bufs->geom || !bufs->binning || !bufs->image || !point_buffer) return fail(RGS_E_INVALID, "null outputs / buffer callbacks");
+	if (io->PN <= 0 || p.P <= 0) return fail(RGS_E_INVALID, "integrate needs at least one Gaussian and one point (the reference returns its fill values)");
+	if (!io->points3D || !io->out_color || !io->out_alpha_integrated || !io->out_color_integrated || !io->out_coordinate2d || !io->out_sdf || !io->radii)
+		return fail(RGS_E_INVALID, "null integrate inputs / outputs");
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	GeomView g;
+	BinView b;
+	ImgView img;
+	const int64_t R = forward_to_binning(&c, p, io->radii, bufs, s, g, b, img);
+	if (R < 0) return R;
+	const int tiles = p.grid_x * p.grid_y;
+	const size_t N = (size_t)p.W * p.H;
+	const int PN = io->PN;
+	IntegrateView v;
+	size_t bytes = 0;
+	for (int pass = 0; pass < 2; pass++) {
+		char* base = nullptr;
+		if (pass == 1) {
+			base = point_buffer(point_buffer_user, bytes);
+			if (!base) return fail(RGS_E_ALLOC, "point buffer callback returned NULL");
+		}
+		Carver cv(base);
+		v.PN = PN;
+		v.points3D = io->points3D;
+		v.invray = cv.take<float>((size_t)p.P * 8);
+		v.masks = cv.take<uint32_t>(integrate_mask_words(R, tiles));
+		v.aux = cv.take<float4>(2 * N);
+		v.overflow = cv.take<int>(1);
+		v.key_in = cv.take<uint32_t>(PN);
+		v.key_out = cv.take<uint32_t>(PN);
+		v.pid_in = cv.take<uint32_t>(PN);
+		v.pid_out = cv.take<uint32_t>(PN);
+		v.pxy = cv.take<float2>(PN);
+		v.pdepth = cv.take<float>(PN);
+		v.sort_temp_bytes = integrate_sort_temp_bytes(PN);
+		v.sort_temp = cv.take<char>(v.sort_temp_bytes);
+		bytes = cv.size();
+	}
+	IntegrateOut out{io->out_color, io->out_alpha_integrated, io->out_color_integrated, io->out_coordinate2d, io->out_sdf};
+	launch_integrate(p, g, b, img, io->radii, v, out, s);
+	if ((rc = debug_sync(&c, s, "integrate")) != RGS_OK) return rc;
+	if (overflowed_pixels) {
+		// rare diagnostic (the reference printf's from the kernel): one more small blocking read
+		int host = 0;
+		RGS_CUDA_TRY(cudaMemcpyAsync(&host, v.overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+		RGS_CUDA_TRY(cudaStreamSynchronize(s));
+		*overflowed_pixels = host;
+	}
 	return R;
 }
 

@@ -249,6 +249,27 @@ void launch_densification_stats(int P, const float* means2D_grad, const int* rad
 void launch_compute_3d_filter(int P, const float* xyz, int n_cams, const float* cams, float focal_length, float* filter_3D, float* max_distance,
                               cudaStream_t s);
 
+// opacity integration at query points (rgs_integrate.cu)
+struct IntegrateView {
+	int PN;
+	const float* points3D;   // [PN,3]
+	float* invray;           // [P,8]  inverse ray-space covariance (6) + well-conditioned flag + pad
+	uint32_t* masks;         // contribution bit masks, integrate_mask_words(R, tiles)
+	float4* aux;             // [2*H*W] per-pixel state phase B needs (median splat plane, last contributor)
+	int* overflow;           // pixels that hit the contributor cap
+	uint32_t *key_in, *key_out, *pid_in, *pid_out;  // [PN] pixel index per point and point ids, before / after the sort
+	float2* pxy;             // [PN]
+	float* pdepth;           // [PN]
+	char* sort_temp;
+	size_t sort_temp_bytes;
+};
+struct IntegrateOut {
+	float *out_color, *out_alpha, *out_color_int, *out_coord, *out_sdf;
+};
+size_t integrate_sort_temp_bytes(int PN);
+size_t integrate_mask_words(int64_t R, int tiles);
+void launch_integrate(const FwdParams& p, GeomView g, BinView b, ImgView img, const int* radii, IntegrateView v, IntegrateOut out, cudaStream_t s);
+
 // fused image-side losses (rgs_image_loss.cu)
 void launch_ssim_l1_forward(int planes, int H, int W, const float* img, const float* gt, float* dmaps, double* sums, cudaStream_t s);
 void launch_ssim_l1_backward(int planes, int H, int W, const float* img, const float* gt, const float* dmaps, float w_ssim, float w_l1,

@@ -300,12 +300,59 @@ torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, tor
 	return present;
 }
 
-// GOF-style opacity integration at query points (rasterize_points.h:83-107): used only by marching-tetrahedra
-// mesh extraction, outside this build's hot path (DESIGN.md "Out of scope").  The symbol is kept so that
-// `GaussianRasterizer.integrate` fails with a clear message instead of an AttributeError.
-py::object IntegrateGaussiansToPointsCUDA(py::args, py::kwargs) {
-	TORCH_CHECK(false, "integrate_gaussians_to_points is not implemented in the B200 rasterizer build (mesh-extraction path, out of scope)");
-	return py::none();
+// GOF-style opacity integration at query points (rasterize_points.h:83-107, rasterize_points.cu:269-388): the call
+// marching-tetrahedra mesh extraction makes once per view.  Same argument list and 10-tuple as the reference
+// (view2gaussian_precomp and subpixel_offset are accepted and unused there as well).
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+IntegrateGaussiansToPointsCUDA(const torch::Tensor& background, const torch::Tensor& points3D, const torch::Tensor& means3D, const torch::Tensor& colors,
+                               const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
+                               const torch::Tensor& cov3D_precomp, const torch::Tensor& view2gaussian_precomp, const torch::Tensor& viewmatrix,
+                               const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const float kernel_size,
+                               const torch::Tensor& subpixel_offset, const int image_height, const int image_width, const torch::Tensor& sh,
+                               const int degree, const torch::Tensor& campos, const bool prefiltered, const bool debug) {
+	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
+		AT_ERROR("means3D must have dimensions (num_points, 3)");
+	}
+	if (points3D.ndimension() != 2 || points3D.size(1) != 3) {
+		AT_ERROR("points3D must have dimensions (num_points, 3)");
+	}
+	TORCH_CHECK(means3D.is_cuda() && points3D.is_cuda(), "means3D / points3D must be CUDA tensors: this rasterizer has no CPU path");
+	const c10::cuda::CUDAGuard guard(means3D.device());
+	const int PN = points3D.size(0), P = means3D.size(0), H = image_height, W = image_width;
+	auto int_opts = means3D.options().dtype(torch::kInt32);
+	auto float_opts = means3D.options().dtype(torch::kFloat32);
+	auto byte_opts = means3D.options().dtype(torch::kByte);
+	const bool run = P != 0 && PN != 0;  // rasterize_points.cu:341: otherwise the fill values below are returned
+	torch::Tensor out_color = run ? torch::empty({9, H, W}, float_opts) : torch::zeros({9, H, W}, float_opts);
+	torch::Tensor radii = run ? torch::empty({P}, int_opts) : torch::zeros({P}, int_opts);
+	torch::Tensor out_alpha_integrated = run ? torch::empty({PN}, float_opts) : torch::full({PN}, 1.0, float_opts);
+	torch::Tensor out_color_integrated = run ? torch::empty({PN, 3}, float_opts) : torch::zeros({PN, 3}, float_opts);
+	torch::Tensor out_coordinate2d = run ? torch::empty({PN, 2}, float_opts) : torch::zeros({PN, 2}, float_opts);
+	torch::Tensor out_sdf = run ? torch::empty({PN}, float_opts) : torch::full({PN}, -1000.0, float_opts);
+	torch::Tensor geomBuffer = torch::empty({0}, byte_opts), binningBuffer = torch::empty({0}, byte_opts), imgBuffer = torch::empty({0}, byte_opts),
+	              pointBuffer = torch::empty({0}, byte_opts);
+	int rendered = 0;
+	if (run) {
+		int M = 0;
+		if (sh.size(0) != 0) M = sh.size(1);
+		CamHolder ch;
+		fill_camera(ch, means3D, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, kernel_size, scale_modifier, H, W, degree, M,
+		            prefiltered, false, true, debug, 0, -1);
+		GaussHolder gh;
+		fill_gaussians(gh, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp);
+		torch::Tensor pts = as_input(points3D, means3D, "points3D");
+		rgs_integrate_io io{PN, pts.data_ptr<float>(), out_color.data_ptr<float>(), out_alpha_integrated.data_ptr<float>(),
+		                    out_color_integrated.data_ptr<float>(), out_coordinate2d.data_ptr<float>(), out_sdf.data_ptr<float>(), radii.data_ptr<int>()};
+		rgs_buffers bufs{resize_cb, &geomBuffer, resize_cb, &binningBuffer, resize_cb, &imgBuffer};
+		int32_t overflowed = 0;
+		const int64_t rc = rgs_integrate(&ch.cam, &gh.g, &io, &bufs, resize_cb, &pointBuffer, debug ? &overflowed : nullptr,
+		                                 at::cuda::getCurrentCUDAStream().stream());
+		check(rc);
+		rendered = (int)rc;
+		if (overflowed > 0) printf("ERROR: Maximal contributors are met in %d pixels. This should be fixed!\n", overflowed);  // forward.cu:1128
+	}
+	return std::make_tuple(rendered, out_color, out_alpha_integrated, out_color_integrated, out_coordinate2d, out_sdf, radii, geomBuffer, binningBuffer,
+	                       imgBuffer);
 }
 
 // ---- multi-GPU extras ---------------------------------------------------------------------------------------------

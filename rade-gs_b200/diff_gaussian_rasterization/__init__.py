@@ -197,7 +197,24 @@ class GaussianRasterizer(nn.Module):
 
     def integrate(self, points3D, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                   cov3D_precomp=None, view2gaussian_precomp=None):
-        """GOF-style opacity integration at query points (reference :239-306).  Outside the accelerated path of
-        this build (marching-tetrahedra mesh extraction only): the exported symbol raises a RuntimeError."""
+        """GOF-style opacity integration at query points (reference :239-306), used by marching-tetrahedra mesh
+        extraction.  Returns ``(color [9,H,W], alpha_integrated [PN], color_integrated [PN,3], point_coordinate [PN,2],
+        point_sdf [PN], radii [P])``; like the reference the call is not differentiable and runs with kernel_size 0."""
+        s = self.raster_settings
         _check_exclusive(shs, colors_precomp, scales, rotations, cov3D_precomp)
-        return _C.integrate_gaussians_to_points(points3D, means3D, means2D, opacities)
+        shs = _absent() if shs is None else shs
+        colors_precomp = _absent() if colors_precomp is None else colors_precomp
+        scales = _absent() if scales is None else scales
+        rotations = _absent() if rotations is None else rotations
+        cov3D_precomp = _absent() if cov3D_precomp is None else cov3D_precomp
+        view2gaussian_precomp = _absent() if view2gaussian_precomp is None else view2gaussian_precomp
+        subpixel_offset = _absent()  # the reference allocates an [H,W,2] zero tensor that its kernel never uses (:265)
+        args = (
+            s.bg, points3D, means3D, colors_precomp, opacities, scales, rotations, s.scale_modifier, cov3D_precomp, view2gaussian_precomp,
+            s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, 0.0, subpixel_offset, s.image_height, s.image_width, shs, s.sh_degree,
+            s.campos, s.prefiltered, s.debug,
+        )
+        with torch.no_grad():
+            (_num_rendered, color, alpha_integrated, color_integrated, point_coordinate, point_sdf, radii,
+             _geom, _binning, _img) = _call_with_dump(_C.integrate_gaussians_to_points, args, s.debug, "snapshot_fw.dump", "forward")
+        return color, alpha_integrated, color_integrated, point_coordinate, point_sdf, radii

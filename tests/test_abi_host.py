@@ -88,7 +88,7 @@ def test_no_cpu_fallback():
         dgr._C.rasterize_gaussians(torch.zeros(3), torch.zeros(4, 2), torch.Tensor([]), torch.ones(4, 1), torch.ones(4, 3), torch.ones(4, 4), 1.0,
                                    torch.Tensor([]), torch.eye(4), torch.eye(4), 0.5, 0.5, 0.0, 32, 32, torch.zeros(4, 1, 3), 0, torch.zeros(3),
                                    False, False, True, False)
-    with pytest.raises(RuntimeError, match="not implemented"):
+    with pytest.raises(RuntimeError, match="no CPU path"):
         r.integrate(m, m, m, torch.ones(4, 1), colors_precomp=torch.ones(4, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
 
 
