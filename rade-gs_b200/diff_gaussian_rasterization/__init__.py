@@ -6,8 +6,8 @@ Public surface kept identical to the reference wrapper
 * ``GaussianRasterizationSettings`` -- NamedTuple, same 15 fields in the same order (ref :171-186);
 * ``GaussianRasterizer(raster_settings)`` with ``forward(means3D, means2D, opacities, shs, colors_precomp,
   scales, rotations, cov3D_precomp)`` returning ``(color, radii, coord, mcoord, depth, mdepth, alpha, normal)``
-  (ref :101, :204-237), ``markVisible(positions)`` (ref :193-202) and ``integrate(...)`` (ref :239-306, not
-  implemented in this build: mesh extraction is outside the accelerated path);
+  (ref :101, :204-237), ``markVisible(positions)`` (ref :193-202) and ``integrate(...)`` (ref :239-306, the
+  opacity integration at query points used by mesh extraction);
 * ``rasterize_gaussians(...)`` functional form (ref :20-42);
 * gradient order of the autograd function ``(means3D, means2D, sh, colors_precomp, opacities, scales,
   rotations, cov3Ds_precomp, None)`` (ref :157-167); ``means2D.grad`` receives ``(d/dx, d/dy, sum |.|)``.
