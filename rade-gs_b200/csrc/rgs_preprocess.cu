@@ -18,61 +18,92 @@ namespace rgs {
 
 // SH -> RGB (forward.cu:23-74).  `sh` points at this Gaussian's [M,3] block; with the split layout (`rest` != NULL)
 // `sh` is its [1,3] coefficient-0 row and `rest` its [M-1,3] block of the higher bands.
-__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ sh, const float* __restrict__ rest, float3 pos, float3 campos,
+__device__ __forceinline__ float3 sh_to_rgb(int deg, int M, const float* __restrict__ sh, const float* __restrict__ rest, float3 pos, float3 campos,
                                             uint8_t& clamp_bits) {
 	float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
 	float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
 	dir.x /= len; dir.y /= len; dir.z /= len;
 
-	float c[48];
-	const int ncoef = (deg + 1) * (deg + 1);
-	if (rest != nullptr) {
-		c[0] = __ldg(sh); c[1] = __ldg(sh + 1); c[2] = __ldg(sh + 2);
-#pragma unroll
-		for (int i = 3; i < 48; i++)
-			if (i < ncoef * 3) c[i] = __ldg(rest + i - 3);
-	} else if ((reinterpret_cast<uintptr_t>(sh) & 15) == 0) {
-		const float4* s4 = reinterpret_cast<const float4*>(sh);
-#pragma unroll
-		for (int i = 0; i < 12; i++) {
-			if (i * 4 < ncoef * 3) {
-				float4 v = __ldg(s4 + i);
-				c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
-			}
-		}
-	} else {
-#pragma unroll
-		for (int i = 0; i < 48; i++)
-			if (i < ncoef * 3) c[i] = __ldg(sh + i);
-	}
-#define SH(k, ch) c[3 * (k) + (ch)]
+	// Coefficients are consumed band by band (3, 9, 15, 21 floats) so that at most one band is live in registers; the
+	// per-channel sum keeps the reference's left-to-right order (forward.cu:39-66) and so the same FMA contraction.
+	const float* hi = rest != nullptr ? rest - 3 : sh;  // coefficient k >= 1 starts at hi + 3k in both layouts
+	// 128-bit loads only when every Gaussian's block is a whole number of float4 (M = 4, 8, 12, 16): no read past a block's end
+	const bool vec = rest == nullptr && ((3 * M) & 3) == 0 && (reinterpret_cast<uintptr_t>(sh) & 15) == 0;
 	float res[3];
 	const float x = dir.x, y = dir.y, z = dir.z;
+	float b[24];
+	// band 0 (+ band 1: floats 0..11 are exactly three aligned float4 in the concatenated layout)
+	if (vec) {
+		const float4* s4 = reinterpret_cast<const float4*>(sh);
+		const float4 v0 = __ldg(s4);
+		b[0] = v0.x; b[1] = v0.y; b[2] = v0.z; b[3] = v0.w;
+		if (deg > 0) {
+			const float4 v1 = __ldg(s4 + 1), v2 = __ldg(s4 + 2);
+			b[4] = v1.x; b[5] = v1.y; b[6] = v1.z; b[7] = v1.w; b[8] = v2.x; b[9] = v2.y; b[10] = v2.z; b[11] = v2.w;
+		}
+	} else {
+		b[0] = __ldg(sh); b[1] = __ldg(sh + 1); b[2] = __ldg(sh + 2);
+		if (deg > 0) {
+#pragma unroll
+			for (int i = 3; i < 12; i++) b[i] = __ldg(hi + i);
+		}
+	}
 #pragma unroll
 	for (int ch = 0; ch < 3; ch++) {
-		float r = kSH0 * SH(0, ch);
-		if (deg > 0) {
-			r = r - kSH1 * y * SH(1, ch) + kSH1 * z * SH(2, ch) - kSH1 * x * SH(3, ch);
-			if (deg > 1) {
-				float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-				r = r + kSH2[0] * xy * SH(4, ch) + kSH2[1] * yz * SH(5, ch) + kSH2[2] * (2.0f * zz - xx - yy) * SH(6, ch) +
-				    kSH2[3] * xz * SH(7, ch) + kSH2[4] * (xx - yy) * SH(8, ch);
-				if (deg > 2) {
-					r = r + kSH3[0] * y * (3.0f * xx - yy) * SH(9, ch) + kSH3[1] * xy * z * SH(10, ch) +
-					    kSH3[2] * y * (4.0f * zz - xx - yy) * SH(11, ch) + kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SH(12, ch) +
-					    kSH3[4] * x * (4.0f * zz - xx - yy) * SH(13, ch) + kSH3[5] * z * (xx - yy) * SH(14, ch) +
-					    kSH3[6] * x * (xx - 3.0f * yy) * SH(15, ch);
-				}
-			}
-		}
-		res[ch] = r + 0.5f;
+		float r = kSH0 * b[ch];
+		if (deg > 0) r = r - kSH1 * y * b[3 + ch] + kSH1 * z * b[6 + ch] - kSH1 * x * b[9 + ch];
+		res[ch] = r;
 	}
-#undef SH
+	if (deg > 1) {
+		const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+		// band 2: floats 12..26 (coefficients 4..8); floats 12..27 are four aligned float4, the last one carries float 27
+		float carry = 0.f;
+		if (vec) {
+			const float4* s4 = reinterpret_cast<const float4*>(sh) + 3;
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const float4 v = __ldg(s4 + i);
+				b[4 * i] = v.x; b[4 * i + 1] = v.y; b[4 * i + 2] = v.z; b[4 * i + 3] = v.w;
+			}
+			carry = b[15];
+		} else {
+#pragma unroll
+			for (int i = 0; i < 15; i++) b[i] = __ldg(hi + 12 + i);
+		}
+#pragma unroll
+		for (int ch = 0; ch < 3; ch++)
+			res[ch] = res[ch] + kSH2[0] * xy * b[ch] + kSH2[1] * yz * b[3 + ch] + kSH2[2] * (2.0f * zz - xx - yy) * b[6 + ch] +
+			          kSH2[3] * xz * b[9 + ch] + kSH2[4] * (xx - yy) * b[12 + ch];
+		if (deg > 2) {
+			// band 3: floats 27..47 (coefficients 9..15)
+			if (vec) {
+				const float4* s4 = reinterpret_cast<const float4*>(sh) + 7;
+				b[0] = carry;
+#pragma unroll
+				for (int i = 0; i < 5; i++) {
+					const float4 v = __ldg(s4 + i);
+					b[1 + 4 * i] = v.x; b[2 + 4 * i] = v.y; b[3 + 4 * i] = v.z; b[4 + 4 * i] = v.w;
+				}
+			} else {
+#pragma unroll
+				for (int i = 0; i < 21; i++) b[i] = __ldg(hi + 27 + i);
+			}
+#pragma unroll
+			for (int ch = 0; ch < 3; ch++)
+				res[ch] = res[ch] + kSH3[0] * y * (3.0f * xx - yy) * b[ch] + kSH3[1] * xy * z * b[3 + ch] +
+				          kSH3[2] * y * (4.0f * zz - xx - yy) * b[6 + ch] + kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * b[9 + ch] +
+				          kSH3[4] * x * (4.0f * zz - xx - yy) * b[12 + ch] + kSH3[5] * z * (xx - yy) * b[15 + ch] +
+				          kSH3[6] * x * (xx - 3.0f * yy) * b[18 + ch];
+		}
+	}
+#pragma unroll
+	for (int ch = 0; ch < 3; ch++) res[ch] += 0.5f;
 	clamp_bits = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
 	return float3{fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f)};
 }
 
-__global__ void __launch_bounds__(256, 3) preprocess_forward_kernel(FwdParams p, GeomView g, int* __restrict__ radii, uint32_t* __restrict__ tile_count) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS) preprocess_forward_kernel(FwdParams p, GeomView g, int* __restrict__ radii, uint32_t* __restrict__ tile_count) {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= p.P) return;
 
@@ -195,9 +226,9 @@ __global__ void __launch_bounds__(256, 3) preprocess_forward_kernel(FwdParams p,
 				if (p.colors_precomp == nullptr) {
 					const float3 campos = {p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]};
 					if (p.shs_rest != nullptr)
-						rgb = sh_to_rgb(p.D, p.shs + (size_t)idx * 3, p.shs_rest + (size_t)idx * (p.M - 1) * 3, p_orig, campos, clamp_bits);
+						rgb = sh_to_rgb(p.D, p.M, p.shs + (size_t)idx * 3, p.shs_rest + (size_t)idx * (p.M - 1) * 3, p_orig, campos, clamp_bits);
 					else
-						rgb = sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, nullptr, p_orig, campos, clamp_bits);
+						rgb = sh_to_rgb(p.D, p.M, p.shs + (size_t)idx * p.M * 3, nullptr, p_orig, campos, clamp_bits);
 				} else {
 					rgb = {p.colors_precomp[3 * idx], p.colors_precomp[3 * idx + 1], p.colors_precomp[3 * idx + 2]};
 				}
@@ -238,7 +269,9 @@ __global__ void __launch_bounds__(256, 3) preprocess_forward_kernel(FwdParams p,
 void launch_preprocess_forward(const FwdParams& p, GeomView g, int* radii, uint32_t* tile_count, cudaStream_t s) {
 	const int threads = 256;
 	const int blocks = (p.P + threads - 1) / threads;
-	preprocess_forward_kernel<<<blocks, threads, 0, s>>>(p, g, radii, tile_count);
+	static const int min_blocks = getenv("RGS_PRE_MINBLOCKS") ? atoi(getenv("RGS_PRE_MINBLOCKS")) : 4;  // 64 registers, 4 CTAs/SM: 5-10% faster than 3 (A/B on C2 / C3)
+	if (min_blocks >= 4) preprocess_forward_kernel<4><<<blocks, threads, 0, s>>>(p, g, radii, tile_count);
+	else preprocess_forward_kernel<3><<<blocks, threads, 0, s>>>(p, g, radii, tile_count);
 	count_launch();
 }
 

