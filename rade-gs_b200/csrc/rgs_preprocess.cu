@@ -48,14 +48,25 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, int M, const float* __restr
 			for (int i = 3; i < 12; i++) b[i] = __ldg(hi + i);
 		}
 	}
+	// The basis polynomials are evaluated BEFORE each band's (layout-dependent) loads and with the reference's expression
+	// trees ((k * y) * (3xx - yy)) * sh: what follows the loads is then a chain of a*b+c steps that can contract in one way
+	// only, so both layouts round identically whatever the compiler does with the two load paths.
+	const float B1 = kSH1 * y, B2 = kSH1 * z, B3 = kSH1 * x;
 #pragma unroll
 	for (int ch = 0; ch < 3; ch++) {
 		float r = kSH0 * b[ch];
-		if (deg > 0) r = r - kSH1 * y * b[3 + ch] + kSH1 * z * b[6 + ch] - kSH1 * x * b[9 + ch];
+		if (deg > 0) r = r - B1 * b[3 + ch] + B2 * b[6 + ch] - B3 * b[9 + ch];
 		res[ch] = r;
 	}
 	if (deg > 1) {
 		const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+		const float B4 = kSH2[0] * xy, B5 = kSH2[1] * yz, B6 = kSH2[2] * (2.0f * zz - xx - yy), B7 = kSH2[3] * xz, B8 = kSH2[4] * (xx - yy);
+		float B9 = 0.f, B10 = 0.f, B11 = 0.f, B12 = 0.f, B13 = 0.f, B14 = 0.f, B15 = 0.f;
+		if (deg > 2) {
+			B9 = kSH3[0] * y * (3.0f * xx - yy); B10 = kSH3[1] * xy * z; B11 = kSH3[2] * y * (4.0f * zz - xx - yy);
+			B12 = kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy); B13 = kSH3[4] * x * (4.0f * zz - xx - yy); B14 = kSH3[5] * z * (xx - yy);
+			B15 = kSH3[6] * x * (xx - 3.0f * yy);
+		}
 		// band 2: floats 12..26 (coefficients 4..8); floats 12..27 are four aligned float4, the last one carries float 27
 		float carry = 0.f;
 		if (vec) {
@@ -71,9 +82,7 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, int M, const float* __restr
 			for (int i = 0; i < 15; i++) b[i] = __ldg(hi + 12 + i);
 		}
 #pragma unroll
-		for (int ch = 0; ch < 3; ch++)
-			res[ch] = res[ch] + kSH2[0] * xy * b[ch] + kSH2[1] * yz * b[3 + ch] + kSH2[2] * (2.0f * zz - xx - yy) * b[6 + ch] +
-			          kSH2[3] * xz * b[9 + ch] + kSH2[4] * (xx - yy) * b[12 + ch];
+		for (int ch = 0; ch < 3; ch++) res[ch] = res[ch] + B4 * b[ch] + B5 * b[3 + ch] + B6 * b[6 + ch] + B7 * b[9 + ch] + B8 * b[12 + ch];
 		if (deg > 2) {
 			// band 3: floats 27..47 (coefficients 9..15)
 			if (vec) {
@@ -90,10 +99,8 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, int M, const float* __restr
 			}
 #pragma unroll
 			for (int ch = 0; ch < 3; ch++)
-				res[ch] = res[ch] + kSH3[0] * y * (3.0f * xx - yy) * b[ch] + kSH3[1] * xy * z * b[3 + ch] +
-				          kSH3[2] * y * (4.0f * zz - xx - yy) * b[6 + ch] + kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * b[9 + ch] +
-				          kSH3[4] * x * (4.0f * zz - xx - yy) * b[12 + ch] + kSH3[5] * z * (xx - yy) * b[15 + ch] +
-				          kSH3[6] * x * (xx - 3.0f * yy) * b[18 + ch];
+				res[ch] = res[ch] + B9 * b[ch] + B10 * b[3 + ch] + B11 * b[6 + ch] + B12 * b[9 + ch] + B13 * b[12 + ch] + B14 * b[15 + ch] +
+				          B15 * b[18 + ch];
 		}
 	}
 #pragma unroll
