@@ -99,7 +99,8 @@ static BinView carve_bin(char* base, size_t R, int tiles, size_t sort_bytes, siz
 	return b;
 }
 
-static ImgView carve_img(char* base, int tiles, size_t N, bool coord, bool depth, size_t* total) {
+static ImgView carve_img(char* base, int grid_x, int grid_y, size_t N, bool coord, bool depth, size_t* total) {
+	const int tiles = grid_x * grid_y;
 	Carver c(base);
 	ImgView v;
 	v.ranges = c.take<uint2>(tiles);
@@ -110,6 +111,7 @@ static ImgView carve_img(char* base, int tiles, size_t N, bool coord, bool depth
 	v.accum_depth = c.take<float>(depth ? N : 0);
 	v.normal_length = c.take<float>((coord || depth) ? N : 0);
 	v.accum_coord = c.take<float>(coord ? 3 * N : 0);
+	v.tile_diff = c.take<int>((size_t)(grid_x + 1) * (grid_y + 1));
 	if (total) *total = c.size();
 	return v;
 }
@@ -205,10 +207,10 @@ static int64_t forward_to_binning(const rgs_camera* cam, const FwdParams& p, int
 
 	// image-side scratch first: needed even when there is nothing to draw (background fill)
 	size_t img_bytes = 0;
-	carve_img(nullptr, tiles, N, p.coord, p.depth, &img_bytes);
+	carve_img(nullptr, p.grid_x, p.grid_y, N, p.coord, p.depth, &img_bytes);
 	char* img_ptr = bufs->image(bufs->image_user, img_bytes);
 	if (!img_ptr) return fail(RGS_E_ALLOC, "image buffer callback returned NULL");
-	img = carve_img(img_ptr, tiles, N, p.coord, p.depth, nullptr);
+	img = carve_img(img_ptr, p.grid_x, p.grid_y, N, p.coord, p.depth, nullptr);
 
 	const size_t scan_bytes = P > 0 ? scan_temp_bytes(P) : 0;
 	size_t geom_bytes = 0;
@@ -220,8 +222,8 @@ static int64_t forward_to_binning(const rgs_camera* cam, const FwdParams& p, int
 	int64_t R = 0;
 	uint32_t max_list = 0;
 	if (P > 0) {
-		RGS_CUDA_TRY(cudaMemsetAsync(img.tile_count, 0, (size_t)tiles * sizeof(uint32_t), s));
-		{ StageScope sc(ST_PREPROCESS, s); launch_preprocess_forward(p, g, radii, img.tile_count, s); }
+		RGS_CUDA_TRY(cudaMemsetAsync(img.tile_diff, 0, (size_t)(p.grid_x + 1) * (p.grid_y + 1) * sizeof(int), s));
+		{ StageScope sc(ST_PREPROCESS, s); launch_preprocess_forward(p, g, radii, img.tile_diff, s); }
 		if ((rc = debug_sync(cam, s, "preprocess")) != RGS_OK) return rc;
 		{ StageScope sc(ST_SCAN, s); launch_tile_scan(p, img, s); }
 		// the one host sync of the forward pass: the instance count sizes the binning buffers and is returned to the
@@ -346,7 +348,7 @@ static int backward_views(const rgs_camera* cam, const rgs_gaussians* gs, const 
 	g = carve_geom(const_cast<char*>(in->geom_buffer), p.P, p.coord, scan_bytes, nullptr);
 	const size_t sort_bytes = in->num_rendered > 0 ? sort_temp_bytes((size_t)in->num_rendered) : 0;
 	b = carve_bin(const_cast<char*>(in->binning_buffer), (size_t)in->num_rendered, p.grid_x * p.grid_y, sort_bytes, nullptr);
-	img = carve_img(const_cast<char*>(in->image_buffer), p.grid_x * p.grid_y, N, p.coord, p.depth, nullptr);
+	img = carve_img(const_cast<char*>(in->image_buffer), p.grid_x, p.grid_y, N, p.coord, p.depth, nullptr);
 	return RGS_OK;
 }
 
@@ -493,7 +495,7 @@ int32_t rgs_debug_get_views(const rgs_camera* cam, int32_t P, int64_t num_render
 	GeomView g = carve_geom(const_cast<char*>(geom_buffer), P, coord, scan_bytes, nullptr);
 	const size_t sort_bytes = num_rendered > 0 ? sort_temp_bytes((size_t)num_rendered) : 0;
 	BinView b = carve_bin(const_cast<char*>(binning_buffer), (size_t)num_rendered, grid_x * grid_y, sort_bytes, nullptr);
-	ImgView img = carve_img(const_cast<char*>(image_buffer), grid_x * grid_y, N, coord, depth, nullptr);
+	ImgView img = carve_img(const_cast<char*>(image_buffer), grid_x, grid_y, N, coord, depth, nullptr);
 	views->point_list = b.point_list;
 	views->point_list_keys = b.keys_sorted;
 	views->tile_ranges = reinterpret_cast<const uint32_t*>(img.ranges);

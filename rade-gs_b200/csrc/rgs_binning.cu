@@ -121,12 +121,29 @@ void launch_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, cons
 // Lists longer than TILE_SORT_CAP (shared-memory capacity) make the host take the radix path above instead.
 // =====================================================================================================================
 
-__global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
-                                                          uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ totals) {
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int grid_x, int grid_y, int* __restrict__ tile_diff, uint32_t* __restrict__ tile_count,
+                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ chunk_base,
+                                                          uint32_t* __restrict__ totals) {
 	__shared__ uint32_t s_warp[32], s_warp2[32];
 	__shared__ uint32_t s_carry, s_carry2, s_max;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tiles = grid_x * grid_y;
 	if (tid == 0) { s_carry = 0; s_carry2 = 0; s_max = 0; }
+	// phase 0: 2D prefix sum of the corner-difference grid preprocess filled -> instances per tile (exact integers).
+	// Rows first (one thread per row walks it), then columns; one CTA, so __syncthreads orders the global accesses.
+	{
+		const int W1 = grid_x + 1;
+		for (int y = tid; y < grid_y; y += 1024) {
+			int run = 0;
+			int* row = tile_diff + (size_t)y * W1;
+			for (int x = 0; x < grid_x; x++) { run += row[x]; row[x] = run; }
+		}
+		__syncthreads();
+		for (int x = tid; x < grid_x; x += 1024) {
+			int run = 0;
+			for (int y = 0; y < grid_y; y++) { run += tile_diff[(size_t)y * W1 + x]; tile_count[(size_t)y * grid_x + x] = (uint32_t)run; }
+		}
+	}
 	__syncthreads();
 	uint32_t local_max = 0;
 	for (int base = 0; base < tiles; base += 1024) {
@@ -173,7 +190,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, const uint32
 }
 
 void launch_tile_scan(const FwdParams& p, ImgView img, cudaStream_t s) {
-	tile_scan_kernel<<<1, 1024, 0, s>>>(p.grid_x * p.grid_y, img.tile_count, img.ranges, img.chunk_base, img.totals);
+	tile_scan_kernel<<<1, 1024, 0, s>>>(p.grid_x, p.grid_y, img.tile_diff, img.tile_count, img.ranges, img.chunk_base, img.totals);
 	count_launch();
 }
 

@@ -86,6 +86,7 @@ struct ImgView {
 	float* accum_depth;   // [N]
 	float* normal_length; // [N]
 	float* accum_coord;   // [3 * N]
+	int* tile_diff;       // [(grid_y+1) * (grid_x+1)] corner increments of the tile rectangles; its 2D prefix sum is tile_count
 };
 
 // ---- small column-major 3x3 algebra ---------------------------------------------------------------
@@ -207,7 +208,7 @@ struct FwdParams {
 	const float *viewmatrix, *projmatrix, *cam_pos, *background;
 };
 
-void launch_preprocess_forward(const FwdParams& p, GeomView g, int* radii, uint32_t* tile_count, cudaStream_t s);
+void launch_preprocess_forward(const FwdParams& p, GeomView g, int* radii, int* tile_diff, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
 
 size_t scan_temp_bytes(int P);
