@@ -130,18 +130,51 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int grid_x, int grid_y,
 	const int tiles = grid_x * grid_y;
 	if (tid == 0) { s_carry = 0; s_carry2 = 0; s_max = 0; }
 	// phase 0: 2D prefix sum of the corner-difference grid preprocess filled -> instances per tile (exact integers).
-	// Rows first (one thread per row walks it), then columns; one CTA, so __syncthreads orders the global accesses.
+	// One CTA, so __syncthreads orders the global accesses.
+	//   rows:    a warp per row, 32 columns at a time (coalesced), inclusive shuffle scan + carry, in place;
+	//   columns: the rows are cut into 32 segments (one per warp); lanes are columns (coalesced).  Each warp leaves the
+	//            running sums of its segment in place and the segment totals in shared memory; after a barrier every
+	//            warp adds the totals of the segments above it and writes the compact [tiles] counts.
 	{
+		__shared__ int s_seg[32][256];
 		const int W1 = grid_x + 1;
-		for (int y = tid; y < grid_y; y += 1024) {
-			int run = 0;
+		for (int y = warp; y < grid_y; y += 32) {
 			int* row = tile_diff + (size_t)y * W1;
-			for (int x = 0; x < grid_x; x++) { run += row[x]; row[x] = run; }
+			int carry = 0;
+			for (int x0 = 0; x0 < grid_x; x0 += 32) {
+				const int x = x0 + lane;
+				int v = x < grid_x ? row[x] : 0;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const int n = __shfl_up_sync(0xffffffffu, v, o);
+					if (lane >= o) v += n;
+				}
+				v += carry;
+				if (x < grid_x) row[x] = v;
+				carry = __shfl_sync(0xffffffffu, v, 31);
+			}
 		}
 		__syncthreads();
-		for (int x = tid; x < grid_x; x += 1024) {
-			int run = 0;
-			for (int y = 0; y < grid_y; y++) { run += tile_diff[(size_t)y * W1 + x]; tile_count[(size_t)y * grid_x + x] = (uint32_t)run; }
+		const int rows_per = (grid_y + 31) / 32;
+		const int ya = min(grid_y, warp * rows_per), yb = min(grid_y, ya + rows_per);
+		for (int xb0 = 0; xb0 < grid_x; xb0 += 256) {  // column blocks of 256 (shared-memory capacity), 32 lanes at a time
+			for (int x0 = xb0; x0 < min(grid_x, xb0 + 256); x0 += 32) {
+				const int x = x0 + lane;
+				int run = 0;
+				if (x < grid_x)
+					for (int y = ya; y < yb; y++) { run += tile_diff[(size_t)y * W1 + x]; tile_diff[(size_t)y * W1 + x] = run; }
+				s_seg[warp][x0 - xb0 + lane] = run;
+			}
+			__syncthreads();
+			for (int x0 = xb0; x0 < min(grid_x, xb0 + 256); x0 += 32) {
+				const int x = x0 + lane;
+				if (x < grid_x) {
+					int off = 0;
+					for (int sgm = 0; sgm < warp; sgm++) off += s_seg[sgm][x0 - xb0 + lane];
+					for (int y = ya; y < yb; y++) tile_count[(size_t)y * grid_x + x] = (uint32_t)(tile_diff[(size_t)y * W1 + x] + off);
+				}
+			}
+			__syncthreads();
 		}
 	}
 	__syncthreads();
