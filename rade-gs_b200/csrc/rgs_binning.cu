@@ -125,10 +125,10 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int grid_x, int grid_y,
                                                           uint2* __restrict__ ranges, uint32_t* __restrict__ chunk_base,
                                                           uint32_t* __restrict__ totals) {
 	__shared__ uint32_t s_warp[32], s_warp2[32];
-	__shared__ uint32_t s_carry, s_carry2, s_max;
+	__shared__ uint32_t s_max;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tiles = grid_x * grid_y;
-	if (tid == 0) { s_carry = 0; s_carry2 = 0; s_max = 0; }
+	if (tid == 0) s_max = 0;
 	// phase 0: 2D prefix sum of the corner-difference grid preprocess filled -> instances per tile (exact integers).
 	// One CTA, so __syncthreads orders the global accesses.
 	//   rows:    a warp per row, 32 columns at a time (coalesced), inclusive shuffle scan + carry, in place;
@@ -178,48 +178,52 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int grid_x, int grid_y,
 		}
 	}
 	__syncthreads();
-	uint32_t local_max = 0;
-	for (int base = 0; base < tiles; base += 1024) {
-		const int t = base + tid;
-		const uint32_t c = t < tiles ? tile_count[t] : 0u;
+	// exclusive scan of the per-tile counts (and of their 32-instance chunk counts): every thread owns a run of
+	// consecutive tiles -- local sums, one block scan of the 1024 partials, then the run is written out
+	const int items = (tiles + 1023) / 1024;
+	const int t0 = min(tiles, tid * items), t1 = min(tiles, t0 + items);
+	uint32_t sum = 0, sum2 = 0, local_max = 0;
+	for (int t = t0; t < t1; t++) {
+		const uint32_t c = tile_count[t];
+		sum += c;
+		sum2 += (c + 31u) >> 5;  // 32-instance chunks of this tile (hit-mask words per pixel block)
 		local_max = max(local_max, c);
-		const uint32_t ch = (c + 31u) >> 5;  // 32-instance chunks of this tile (hit-mask words per pixel block)
-		uint32_t v = c, v2 = ch;  // inclusive warp scans
+	}
+	uint32_t v = sum, v2 = sum2;  // inclusive warp scans
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+		const uint32_t n2 = __shfl_up_sync(0xffffffffu, v2, o);
+		if (lane >= o) { v += n; v2 += n2; }
+	}
+	if (lane == 31) { s_warp[warp] = v; s_warp2[warp] = v2; }
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = s_warp[lane], w2 = s_warp2[lane];
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
-			const uint32_t n2 = __shfl_up_sync(0xffffffffu, v2, o);
-			if (lane >= o) { v += n; v2 += n2; }
+			const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
+			const uint32_t n2 = __shfl_up_sync(0xffffffffu, w2, o);
+			if (lane >= o) { w += n; w2 += n2; }
 		}
-		if (lane == 31) { s_warp[warp] = v; s_warp2[warp] = v2; }
-		__syncthreads();
-		if (warp == 0) {
-			uint32_t w = s_warp[lane], w2 = s_warp2[lane];
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
-				const uint32_t n2 = __shfl_up_sync(0xffffffffu, w2, o);
-				if (lane >= o) { w += n; w2 += n2; }
-			}
-			s_warp[lane] = w;
-			s_warp2[lane] = w2;
-		}
-		__syncthreads();
-		const uint32_t incl = s_carry + v + (warp > 0 ? s_warp[warp - 1] : 0u);
-		const uint32_t incl2 = s_carry2 + v2 + (warp > 0 ? s_warp2[warp - 1] : 0u);
-		if (t < tiles) {
-			ranges[t] = c ? make_uint2(incl - c, incl) : make_uint2(0u, 0u);  // empty tiles stay (0,0) like the reference's memset
-			chunk_base[t] = incl2 - ch;
-		}
-		__syncthreads();
-		if (tid == 1023) { s_carry = incl; s_carry2 = incl2; }
-		__syncthreads();
+		s_warp[lane] = w;
+		s_warp2[lane] = w2;
+	}
+	__syncthreads();
+	uint32_t run = v - sum + (warp > 0 ? s_warp[warp - 1] : 0u);
+	uint32_t run2 = v2 - sum2 + (warp > 0 ? s_warp2[warp - 1] : 0u);
+	for (int t = t0; t < t1; t++) {
+		const uint32_t c = tile_count[t];
+		ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);  // empty tiles stay (0,0) like the reference's memset
+		chunk_base[t] = run2;
+		run += c;
+		run2 += (c + 31u) >> 5;
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
 	if (lane == 0) atomicMax(&s_max, local_max);
 	__syncthreads();
-	if (tid == 0) { totals[0] = s_carry; totals[1] = s_max; }
+	if (tid == 0) { totals[0] = s_warp[31]; totals[1] = s_max; }
 }
 
 void launch_tile_scan(const FwdParams& p, ImgView img, cudaStream_t s) {
