@@ -209,7 +209,7 @@ def main():
                                                     sc.tanfovx, sc.tanfovy, 0.0, grads["color"], grads["coord"], grads["mcoord"], grads["depth"],
                                                     grads["mdepth"], grads["alpha"], grads["normal"], out[5], sc.shs, 3, sc.campos, out[9], out[0],
                                                     out[10], out[11], out[4], coord, depth, False, slab[0], slab[1])
-        dist.all_reduce(acc)
+        multigpu.exchange_sum_(acc)
         g = C.rasterize_gaussians_backward_preprocess(acc, sc.bg, sc.means3D, out[8], E, sc.opacities, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix,
                                                       sc.projmatrix, sc.tanfovx, sc.tanfovy, 0.0, H, W, sc.shs, 3, sc.campos, out[9], coord, depth, False)
         return {"num_rendered": out[0]}, g

@@ -14,6 +14,7 @@ add up to the single-GPU answer.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Sequence, Tuple
 
 import torch
@@ -68,10 +69,57 @@ def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
+def exchange_sum_(acc: torch.Tensor, group=None, mode: str | None = None) -> torch.Tensor:
+    """Sum of the slab-local accumulator rows [P, stride] over the ranks, in place, bit-identical on every rank.
+
+    ``dense``: one all-reduce of the whole tensor.  ``sparse``: a rank's rows are zero for every Gaussian that does not reach
+    its slab (with 8 slabs a splat touches 1.25 of them on average), so each rank ships only its non-zero rows -- index +
+    row, one all-gather -- and every rank rebuilds the sum by adding the ranks' rows in rank order (fixed order: same bits
+    everywhere, like an all-reduce).  ``auto`` (default, or ``RGS_GRAD_EXCHANGE``): sparse from 4 ranks on, and only while
+    the gathered rows are smaller than what a ring all-reduce moves.
+    """
+    if not (dist.is_available() and dist.is_initialized()):
+        return acc
+    W = dist.get_world_size(group)
+    if W == 1:
+        return acc
+    mode = mode or os.environ.get("RGS_GRAD_EXCHANGE", "auto")
+    if mode == "dense" or (mode == "auto" and W < 4):
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        return acc
+    idx = torch.nonzero((acc != 0).any(dim=1)).squeeze(1)
+    n_mine = torch.tensor([idx.numel()], dtype=torch.int64, device=acc.device)
+    n_all = [torch.zeros_like(n_mine) for _ in range(W)]
+    dist.all_gather(n_all, n_mine, group=group)
+    counts = [int(c) for c in torch.cat(n_all).tolist()]  # same list on every rank: the branch below is taken by all or none
+    maxn, stride = max(counts), acc.shape[1]
+    if mode == "auto" and W * maxn * (stride + 1) > 2 * (W - 1) / W * acc.numel():
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        return acc
+    rows = torch.zeros(maxn, stride, dtype=acc.dtype, device=acc.device)
+    ids = torch.zeros(maxn, dtype=torch.int32, device=acc.device)
+    rows[: idx.numel()] = acc[idx]
+    ids[: idx.numel()] = idx.to(torch.int32)
+    rows_all = torch.empty(W * maxn, stride, dtype=acc.dtype, device=acc.device)
+    ids_all = torch.empty(W * maxn, dtype=torch.int32, device=acc.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(rows_all, rows, group=group)
+        dist.all_gather_into_tensor(ids_all, ids, group=group)
+    else:  # gloo (CPU tests) has no flat all-gather
+        dist.all_gather(list(rows_all.view(W, maxn, stride).unbind(0)), rows, group=group)
+        dist.all_gather(list(ids_all.view(W, maxn).unbind(0)), ids, group=group)
+    acc.zero_()
+    for r in range(W):  # rank order, own rows included: indices are unique within a rank, so each add is deterministic
+        k = counts[r]
+        if k:
+            acc.index_add_(0, ids_all[r * maxn: r * maxn + k].long(), rows_all[r * maxn: r * maxn + k])
+    return acc
+
+
 def backward_two_stage(stage1_render: Callable[[], torch.Tensor], stage2_preprocess: Callable[[torch.Tensor], tuple], group=None):
-    """slab-local scatter -> one all-reduce -> replicated parameter gradients."""
+    """slab-local scatter -> one exchange of the accumulator rows -> replicated parameter gradients."""
     acc = stage1_render()
-    allreduce_sum_(acc, group)
+    exchange_sum_(acc, group)
     return stage2_preprocess(acc)
 
 

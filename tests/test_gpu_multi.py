@@ -12,7 +12,8 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, outdir):
+def _worker(rank, world, port, outdir, exchange):
+    os.environ["RGS_GRAD_EXCHANGE"] = exchange
     for p in (os.path.join(ROOT, "rade-gs_b200"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     import torch.distributed as dist
@@ -56,11 +57,13 @@ def _worker(rank, world, port, outdir):
         dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_equals_single(tmp_path):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world,exchange", [(2, "auto"), (2, "sparse"), (4, "auto"), (8, "auto")])
+def test_sharded_equals_single(world, exchange, tmp_path):
+    """world ranks over NCCL against the single-GPU answer; `auto` = dense all-reduce below 4 ranks, sparse row exchange above."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000 + world, str(tmp_path), exchange), nprocs=world, join=True)
     res = np.load(tmp_path / "res.npy", allow_pickle=True).item()
     for k in ("color", "depth", "normal", "coord"):
         assert res[k][0] == 0.0, (k, res[k])          # slabs reproduce the single-GPU image bit for bit

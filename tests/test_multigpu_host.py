@@ -123,3 +123,41 @@ def test_gather_image_is_differentiable_across_two_ranks(tmp_path):
         assert torch.allclose(d["grad"][:, r0:r1], want[:, r0:r1])  # the rows this rank's backward consumes
         covered += r1 - r0
     assert covered == 40
+
+
+def _exchange_worker(rank, world, port, tmpdir):
+    sys.path.insert(0, os.path.join(ROOT, "rade-gs_b200"))
+    from rade_gs_b200 import multigpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, stride = 5000, 16
+        out = {}
+        for case, density in (("typical", 0.3), ("empty_rank", 0.0 if rank == 1 else 0.4), ("full", 1.0)):
+            g = torch.Generator().manual_seed(100 + 7 * rank + len(case))
+            acc = torch.randn(P, stride, generator=g)
+            acc[torch.rand(P, generator=g) >= density] = 0.0  # rows of Gaussians that do not reach this rank's slab
+            if density > 0:
+                acc[17] = float(rank + 1)  # a row every rank contributes to
+            out[case + "_in"] = acc.clone()
+            out[case + "_sparse"] = multigpu.exchange_sum_(acc.clone(), mode="sparse")
+            out[case + "_dense"] = multigpu.exchange_sum_(acc.clone(), mode="dense")
+            out[case + "_auto"] = multigpu.exchange_sum_(acc.clone())
+        torch.save(out, os.path.join(tmpdir, f"exchange{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sparse_row_exchange_equals_the_all_reduce(world, tmp_path):
+    port = 33500 + (os.getpid() % 2000) + world
+    mp.spawn(_exchange_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"exchange{r}.pt") for r in range(world)]
+    for case in ("typical", "empty_rank", "full"):
+        total = sum(r[case + "_in"].double() for r in res)
+        for r in res:
+            assert torch.equal(r[case + "_sparse"], res[0][case + "_sparse"])  # same bits on every rank, like an all-reduce
+            assert torch.allclose(r[case + "_sparse"].double(), total, rtol=1e-6, atol=1e-6)
+            assert torch.allclose(r[case + "_dense"].double(), total, rtol=1e-6, atol=1e-6)
+            assert torch.allclose(r[case + "_auto"].double(), total, rtol=1e-6, atol=1e-6)
