@@ -72,19 +72,21 @@ def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
 def exchange_sum_(acc: torch.Tensor, group=None, mode: str | None = None) -> torch.Tensor:
     """Sum of the slab-local accumulator rows [P, stride] over the ranks, in place, bit-identical on every rank.
 
-    ``dense``: one all-reduce of the whole tensor.  ``sparse``: a rank's rows are zero for every Gaussian that does not reach
-    its slab (with 8 slabs a splat touches 1.25 of them on average), so each rank ships only its non-zero rows -- index +
-    row, one all-gather -- and every rank rebuilds the sum by adding the ranks' rows in rank order (fixed order: same bits
-    everywhere, like an all-reduce).  ``auto`` (default, or ``RGS_GRAD_EXCHANGE``): sparse from 4 ranks on, and only while
-    the gathered rows are smaller than what a ring all-reduce moves.
+    ``dense`` (default, or ``RGS_GRAD_EXCHANGE``): one all-reduce of the whole tensor.
+    ``sparse`` (opt-in): a rank's rows are zero for every Gaussian that does not reach its slab (with 8 slabs a splat touches
+    1.25 of them on average), so each rank ships only its non-zero rows -- index + row, one all-gather -- and every rank
+    rebuilds the sum by adding the ranks' rows in rank order (fixed order: same bits everywhere, like an all-reduce).
+    Measured on 8 B200 at C2 it LOSES to NCCL's all-reduce (1.67 vs 1.43 ms per step, profiles/r01_bench_ours_n8*.json): the
+    two size exchanges with their host synchronisations and eight index_add_ passes cost more than the 0.5 ms all-reduce
+    they replace.  Kept because the control flow is the starting point for a fused device-side exchange (no host syncs).
     """
     if not (dist.is_available() and dist.is_initialized()):
         return acc
     W = dist.get_world_size(group)
     if W == 1:
         return acc
-    mode = mode or os.environ.get("RGS_GRAD_EXCHANGE", "auto")
-    if mode == "dense" or (mode == "auto" and W < 4):
+    mode = mode or os.environ.get("RGS_GRAD_EXCHANGE", "dense")
+    if mode != "sparse":
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
         return acc
     idx = torch.nonzero((acc != 0).any(dim=1)).squeeze(1)
@@ -93,9 +95,6 @@ def exchange_sum_(acc: torch.Tensor, group=None, mode: str | None = None) -> tor
     dist.all_gather(n_all, n_mine, group=group)
     counts = [int(c) for c in torch.cat(n_all).tolist()]  # same list on every rank: the branch below is taken by all or none
     maxn, stride = max(counts), acc.shape[1]
-    if mode == "auto" and W * maxn * (stride + 1) > 2 * (W - 1) / W * acc.numel():
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
-        return acc
     rows = torch.zeros(maxn, stride, dtype=acc.dtype, device=acc.device)
     ids = torch.zeros(maxn, dtype=torch.int32, device=acc.device)
     rows[: idx.numel()] = acc[idx]

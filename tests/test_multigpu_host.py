@@ -143,7 +143,7 @@ def _exchange_worker(rank, world, port, tmpdir):
             out[case + "_in"] = acc.clone()
             out[case + "_sparse"] = multigpu.exchange_sum_(acc.clone(), mode="sparse")
             out[case + "_dense"] = multigpu.exchange_sum_(acc.clone(), mode="dense")
-            out[case + "_auto"] = multigpu.exchange_sum_(acc.clone())
+            out[case + "_auto"] = multigpu.exchange_sum_(acc.clone())  # default: dense
         torch.save(out, os.path.join(tmpdir, f"exchange{rank}.pt"))
     finally:
         dist.destroy_process_group()
