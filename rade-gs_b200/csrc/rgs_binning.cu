@@ -109,8 +109,10 @@ void launch_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, cons
 // The reference sorts all R instances globally on 45-bit (tile | depth) keys: six 8-bit onesweep passes, each
 // reading and writing 12 B per instance.  The same total order is (tile, depth bits, Gaussian index), so it can be
 // produced with one bucketing step and one local sort instead:
-//   1. preprocess counts instances per tile (one red.global.add per (splat, tile));
-//   2. tile_scan_kernel: exclusive scan of the T counters -> ranges[tile] = [start, end), num_rendered, longest list;
+//   1. preprocess marks every splat's tile rectangle with +1 / -1 at its four corners on a (grid_y+1) x (grid_x+1)
+//      difference grid (4 red.global.add per splat, whatever the rectangle's size);
+//   2. tile_scan_kernel: 2D prefix sum of that grid = instances per tile, then the exclusive scan of the T counts ->
+//      ranges[tile] = [start, end), num_rendered, longest list;
 //   3. scatter_kernel: every instance takes a slot inside its tile's segment (counter counted back down) and
 //      stores the 64-bit local key (depth bits << 32 | Gaussian index) -- 8 B written once;
 //   4. tile_sort_kernel: one CTA per tile loads its segment into shared memory, merge-sorts the 64-bit keys

@@ -79,7 +79,7 @@ struct BinView {
 
 struct ImgView {
 	uint2* ranges;        // [tiles]
-	uint32_t* tile_count; // [tiles] instances per tile (tile-bucket binning); counted down to 0 by the scatter
+	uint32_t* tile_count; // [tiles] instances per tile (written by tile_scan_kernel from tile_diff); counted down to 0 by the scatter
 	uint32_t* totals;     // [2]     num_rendered, longest tile list
 	uint32_t* chunk_base; // [tiles] first 32-instance chunk of each tile in BinView::hitmask (exclusive scan of ceil(n/32))
 	uint32_t* n_contrib;  // [2 * N]
