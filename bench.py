@@ -45,23 +45,59 @@ METRIC = "Mpix/s fwd+bwd @1M splats 1600x1200"
 # ---- clocks ----------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """nvidia-smi sampled in a thread during the timed region (B200_PROFILING.md 'clocks' line)."""
+    """SM clock / throttle reasons sampled in a thread during the timed region (B200_PROFILING.md 'clocks' line).
+
+    NVML through pynvml (a sample costs microseconds, so even a 50 ms timed region gets several); `nvidia-smi` as the
+    fallback when NVML cannot be opened (one sample per ~100 ms process spawn)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    # nvmlClocksEventReason* bit masks (nvml.h)
+    REASON_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.source = "nvidia-smi"
+        self._nvml, self._h = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            phys = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(v.strip().isdigit() for v in vis.split(",")) and index < len(vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)  # probe
+            self._nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self._nvml, self._h = None, None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._h
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = 0.0
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        bits = int(get(h))
+        flags = {name: ("Active" if bits & mask else "Not Active") for name, mask in self.REASON_BITS}
+        return [str(sm), str(mx), str(pw), flags["hw_slowdown"], flags["hw_thermal_slowdown"], flags["sw_thermal_slowdown"], flags["sw_power_cap"]]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
-                pass
-            self._stop.wait(0.1)
+                if self._nvml is not None:  # NVML misbehaved: fall back for the rest of the run
+                    self._nvml, self.source = None, "nvidia-smi"
+            self._stop.wait(0.004 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -81,7 +117,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": self.source}
 
 
 # ---- implementations under test ----------------------------------------------------------------------------------
