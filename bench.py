@@ -5,30 +5,42 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step is one pass of the hot path over one synthetic camera: `_C.rasterize_gaussians` followed by
-`_C.rasterize_gaussians_backward` with fixed upstream gradients.  Prints ONE JSON line (rank 0):
-  value        W*H*K / t  with every input resident in HBM (device-timed, max over ranks)
+`_C.rasterize_gaussians_backward` with fixed upstream gradients.  Prints ONE JSON line (rank 0).
+
+Protocol (median of >= 20 timed iterations after >= 5 warm-ups):
+  * a *window* is EXACTLY `--steps` iterations bracketed by barrier + torch.cuda.synchronize() on both sides, with a CUDA
+    event between consecutive iterations (on the launching stream); per iteration the time is the MAX over ranks;
+  * windows are repeated until at least `--min-time` seconds (default 0.5) and at least 20 iterations have been timed;
+  * `ms_per_step` = MEDIAN of all per-iteration times, `value` = W*H / that; min / median / max and the per-window means
+    are in `timing` so a perturbed window is visible instead of being averaged in;
+  * SM clocks / throttle reasons are sampled by a separate PROCESS (NVML, no GIL contention with the timed loop) that
+    runs during every timed phase of the run.
+  value        inputs resident in HBM
   e2e          same metric through the public autograd API (`GaussianRasterizer`, what render() calls) with the
                step's host inputs -- camera matrices and the 8-bit ground-truth image -- copied from pinned host
-               memory inside the timed region and the loss read back to the host every step
+               memory inside the timed region and the loss read back to the host every step; same protocol
   roofline     dominant kernel (backward render): algorithmic bytes / its average launch duration,
-               measured with CUDA events the library records on the launching stream in a second timed pass
+               measured live with CUDA events the library records on the launching stream; `traffic` and the
+               instruction count behind `roofline_issue` are REPLAYED from the committed ncu capture (labelled so)
   cpu_baseline the CPU oracle port (oracle/oracle.c, 1 thread) on a bounded sample of the same workload, plus the
                pure-torch config[0] plumbing timing -- reported, not a target
 `--impl reference` times the reference's own CUDA rasterizer (oracle/_ref/ref_dgr_C.so, built from /root/reference
 by oracle/build_ref.py) on the same config through the same harness: the reference has NO CPU implementation of
-this path, so its arm runs where it can -- on the GPU (see DESIGN.md "Measurement").
-N > 1: tile rows of the one image are sharded over the ranks (strong scaling), one NCCL all-reduce of the
-screen-space gradient rows per backward.
+this path, so its arm runs where it can -- on the GPU (see DESIGN.md "Measurement").  That arm
+never imports the product's extension modules.
+N > 1: tile rows of the one image are sharded over the ranks (strong scaling); the screen-space gradient rows are
+exchanged once per backward.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
 import sys
-import threading
+import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -40,84 +52,96 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 METRIC = "Mpix/s fwd+bwd @1M splats 1600x1200"
+SM_COUNT = 148
 
 
 # ---- clocks ----------------------------------------------------------------------------------------------------
 
-class ClockSampler:
-    """SM clock / throttle reasons sampled in a thread during the timed region (B200_PROFILING.md 'clocks' line).
-
-    NVML through pynvml (a sample costs microseconds, so even a 50 ms timed region gets several); `nvidia-smi` as the
-    fallback when NVML cannot be opened (one sample per ~100 ms process spawn)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    # nvmlClocksEventReason* bit masks (nvml.h)
-    REASON_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
-
-    def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
-        self.source = "nvidia-smi"
-        self._nvml, self._h = None, None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            phys = index
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-            if vis and all(v.strip().isdigit() for v in vis.split(",")) and index < len(vis.split(",")):
-                phys = int(vis.split(",")[index])
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)  # probe
-            self._nvml, self.source = pynvml, "nvml"
-        except Exception:
-            self._nvml, self._h = None, None
-
-    def _sample_nvml(self):
-        n, h = self._nvml, self._h
-        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
-        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+_SAMPLER_SRC = r"""
+import sys, time
+idx, path = int(sys.argv[1]), sys.argv[2]
+import pynvml as n
+n.nvmlInit()
+h = n.nvmlDeviceGetHandleByIndex(idx)
+get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+with open(path, "w", buffering=1) as f:
+    f.write("nvml\n")
+    while True:
         try:
             pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
         except Exception:
             pw = 0.0
-        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        bits = int(get(h))
-        flags = {name: ("Active" if bits & mask else "Not Active") for name, mask in self.REASON_BITS}
-        return [str(sm), str(mx), str(pw), flags["hw_slowdown"], flags["hw_thermal_slowdown"], flags["sw_thermal_slowdown"], flags["sw_power_cap"]]
+        f.write("%d,%d,%.1f,%d\n" % (n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx, pw, int(get(h))))
+        time.sleep(0.01)
+"""
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                if self._nvml is not None:
-                    self.rows.append(self._sample_nvml())
-                else:
-                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                         capture_output=True, text=True, timeout=5).stdout.strip()
-                    if out:
-                        self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                if self._nvml is not None:  # NVML misbehaved: fall back for the rest of the run
-                    self._nvml, self.source = None, "nvidia-smi"
-            self._stop.wait(0.004 if self._nvml is not None else 0.1)
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed regions by a separate process (B200_PROFILING.md 'clocks'
+    line): NVML every 10 ms in a helper python process; `nvidia-smi -lms` as the fallback.  Nothing of it runs in this
+    process, so the timed loop does not share the GIL with it."""
+    REASON_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        phys = index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")) and index < len(vis.split(",")):
+            phys = int(vis.split(",")[index])
+        self.index, self.proc, self.source = phys, None, None
+        fd, self.path = tempfile.mkstemp(prefix="rgs_clocks_", suffix=".csv")
+        os.close(fd)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.index), self.path], stdout=subprocess.DEVNULL,
+                                         stderr=subprocess.DEVNULL)
+            t0 = time.time()
+            while time.time() - t0 < 10.0 and self.proc.poll() is None and os.path.getsize(self.path) == 0:
+                time.sleep(0.02)
+            if self.proc.poll() is not None or os.path.getsize(self.path) == 0:
+                raise RuntimeError("nvml sampler did not start")
+            self.source = "nvml (separate process, 10 ms)"
+        except Exception:
+            if self.proc is not None and self.proc.poll() is None:
+                self.proc.kill()
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi -lms 50 (separate process)"
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.terminate()           # the exact PID we started
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows), "source": self.source}
+        sm, mx, reasons, n = [], [], set(), 0
+        try:
+            for ln in open(self.path):
+                c = [x.strip() for x in ln.strip().split(",")]
+                if len(c) < 4 or not c[0].replace(".", "").isdigit():
+                    continue
+                n += 1
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+                if len(c) == 4:     # nvml helper: bit mask
+                    bits = int(c[3])
+                    reasons |= {name for name, mask in self.REASON_BITS if bits & mask}
+                else:               # nvidia-smi: Active / Not Active columns
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": n, "source": self.source}
 
 
 # ---- implementations under test ----------------------------------------------------------------------------------
@@ -157,7 +181,6 @@ class _RefFunction(torch.autograd.Function):
 
 def cpu_baseline():
     """Bounded CPU work (about 10-20 s): the oracle port on a C2-density sample + config[0] torch plumbing."""
-    import numpy as np
     import oracle
     from rade_gs_b200 import scenes
     Wd, Hd, P = 400, 300, 62_500   # 1/16 of C2's pixels and splats, same focal-per-pixel density (f scaled by 1/4)
@@ -198,6 +221,24 @@ def cpu_baseline():
     return res
 
 
+# SURVEY.md 8d per-variant constants: (A_v gather bytes per instance, O_v fwd bytes per pixel, I_v bwd bytes per pixel, G_v grad floats per Gaussian)
+VARIANT_BYTES = {(False, False): (36, 24, 28, 10), (False, True): (60, 52, 68, 16), (True, False): (84, 76, 92, 22), (True, True): (96, 88, 104, 25)}
+
+
+def algorithmic_bytes(P, Pv, R, N, T, M, coord, depth):
+    """SURVEY.md 8d, per stage, for one step."""
+    A, O, I, G = VARIANT_BYTES[(coord, depth)]
+    tiles_bits = max(1, math.ceil(math.log2(max(T, 2))))
+    sort = math.ceil((32 + tiles_bits) / 8) * 2 * 12 * R
+    return {
+        "preprocess_forward": P * (44 + 12 * M + 4) + Pv * (A + 35),
+        "binning": 8 * P + 12 * R + sort,
+        "render_forward": R * (A + 4) + N * O + 8 * T,
+        "render_backward": R * (A + 4) + N * I + 8 * T + 4 * G * Pv,
+        "preprocess_backward": Pv * (12 + 24 + 28 + 4 * G + 12 * M + 12 * M + 12 + 12 + 16 + 24),
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,9 +246,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
+    ap.add_argument("--min-time", type=float, default=0.5, help="seconds of timed work per measured quantity (windows of --steps are repeated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    a.steps = max(a.steps, 1)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,22 +261,29 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    multi = world > 1 and a.impl == "ours"
+    ours = a.impl == "ours"
+    multi = world > 1 and ours
     if multi:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    from rade_gs_b200 import multigpu, rawapi, scenes
+    from rade_gs_b200 import rawapi, scenes   # pure-Python helpers (scene synthesis, the two raw _C calls): no extension is loaded by them
     C = load_impl(a.impl)
+    dgr = multigpu = None
+    if ours:
+        import diff_gaussian_rasterization as dgr
+        from rade_gs_b200 import multigpu
     sc_cpu, coord, depth = scenes.make_config(a.config)
     sc = sc_cpu.to(dev)
     W, H, P = sc.width, sc.height, sc.means3D.shape[0]
     grads = scenes.make_upstream_grads(H, W, device=dev)
     grid_y = (H + 15) // 16
+    tiles = ((W + 15) // 16) * grid_y
     slab = multigpu.partition_tile_rows(grid_y, world)[rank] if multi else (0, grid_y)
     E = torch.Tensor([])
+    exchange = multigpu.GradExchange(P, C.grad_stride(coord, depth), dev) if multi else None
 
     def step_resident():
         if not multi:
@@ -241,11 +291,10 @@ def main():
             return f, rawapi.backward(C, sc, f, grads)
         out = C.rasterize_gaussians_slab(sc.bg, sc.means3D, E, sc.opacities, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix, sc.projmatrix,
                                          sc.tanfovx, sc.tanfovy, 0.0, H, W, sc.shs, 3, sc.campos, False, coord, depth, False, slab[0], slab[1])
-        acc = C.rasterize_gaussians_backward_render(sc.bg, sc.means3D, out[8], E, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix, sc.projmatrix,
-                                                    sc.tanfovx, sc.tanfovy, 0.0, grads["color"], grads["coord"], grads["mcoord"], grads["depth"],
-                                                    grads["mdepth"], grads["alpha"], grads["normal"], out[5], sc.shs, 3, sc.campos, out[9], out[0],
-                                                    out[10], out[11], out[4], coord, depth, False, slab[0], slab[1])
-        multigpu.exchange_sum_(acc)
+        acc = exchange.backward_render(C, sc.bg, sc.means3D, out[8], E, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix, sc.projmatrix,
+                                       sc.tanfovx, sc.tanfovy, 0.0, grads["color"], grads["coord"], grads["mcoord"], grads["depth"],
+                                       grads["mdepth"], grads["alpha"], grads["normal"], out[5], sc.shs, 3, sc.campos, out[9], out[0],
+                                       out[10], out[11], out[4], coord, depth, False, slab[0], slab[1])
         g = C.rasterize_gaussians_backward_preprocess(acc, sc.bg, sc.means3D, out[8], E, sc.opacities, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix,
                                                       sc.projmatrix, sc.tanfovx, sc.tanfovy, 0.0, H, W, sc.shs, 3, sc.campos, out[9], coord, depth, False)
         return {"num_rendered": out[0]}, g
@@ -255,113 +304,150 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            r = fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if multi:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, r
+    def measure(fn):
+        """Windows of exactly --steps iterations (barrier + synchronize on both sides, CUDA events between iterations on the
+        launching stream, max over ranks per iteration) until --min-time seconds and >= 20 iterations are on record."""
+        iters, windows, last, total = [], [], None, 0.0
+        while True:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+            barrier()
+            ev[0].record()
+            for i in range(a.steps):
+                last = fn()
+                ev[i + 1].record()
+            barrier()
+            t = torch.tensor([ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)] + [ev[0].elapsed_time(ev[a.steps])], device=dev, dtype=torch.float64)
+            if multi:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t = t.tolist()
+            iters += t[:-1]
+            windows.append(t[-1] / a.steps)
+            total += t[-1] * 1e-3
+            if (total >= a.min_time and len(iters) >= 20) or len(windows) >= 200:
+                break
+        med = statistics.median(iters)
+        return {"ms": med, "min_ms": min(iters), "max_ms": max(iters), "iterations": len(iters), "windows": len(windows),
+                "window_mean_ms": {"min": min(windows), "median": statistics.median(windows), "max": max(windows)}, "timed_s": total}, last
 
-    # ---- resident-input number ----
-    for _ in range(a.warmup):
-        last = step_resident()
-    launches0 = C.launch_count() if a.impl == "ours" else 0
-    with ClockSampler(local) as clk:
-        ms, last = timed(step_resident, a.steps)
-    launches = (C.launch_count() - launches0) if a.impl == "ours" else None
-    ms_per_step = ms / a.steps
-    value = W * H / (ms_per_step * 1e-3) / 1e6
-    R = int(last[0]["num_rendered"])
+    import contextlib
+    with (ClockSampler(local) if rank == 0 else contextlib.nullcontext()) as clk:
+        # ---- resident-input number ----
+        for _ in range(a.warmup):
+            last = step_resident()
+        launches0 = C.launch_count() if ours else 0
+        t_res, last = measure(step_resident)
+        launches = (C.launch_count() - launches0) if ours else None
+        ms_per_step = t_res["ms"]
+        value = W * H / (ms_per_step * 1e-3) / 1e6
+        R = int(last[0]["num_rendered"])
 
-    # ---- end-to-end number: public autograd API, host inputs copied in, loss copied out ----
-    import diff_gaussian_rasterization as dgr
-    # Host inputs of one training step, as train.py has them: the camera (matrices, position, background) and the
-    # ground-truth photograph, 8 bits per channel like every dataset the reference reads (PNG/JPEG).  Depth / normal
-    # supervision in RaDe-GS is self-consistency between rendered maps, so no ground truth is shipped for them.
-    host = {"view": sc_cpu.viewmatrix.pin_memory(), "proj": sc_cpu.projmatrix.pin_memory(), "campos": sc_cpu.campos.pin_memory(),
-            "bg": sc_cpu.bg.pin_memory(), "gt_color": (torch.rand(3, H, W) * 255).to(torch.uint8).pin_memory()}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
-    leaves = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
-    copy_stream = torch.cuda.Stream(device=dev)
-    r0, r1 = min(slab[0] * 16, H), min(slab[1] * 16, H)
+        # ---- end-to-end number: public autograd API, host inputs copied in, loss copied out ----
+        # Host inputs of one training step, as train.py has them: the camera (matrices, position, background) and the
+        # ground-truth photograph, 8 bits per channel like every dataset the reference reads (PNG/JPEG).  Depth / normal
+        # supervision in RaDe-GS is self-consistency between rendered maps, so no ground truth is shipped for them.
+        host = {"view": sc_cpu.viewmatrix.pin_memory(), "proj": sc_cpu.projmatrix.pin_memory(), "campos": sc_cpu.campos.pin_memory(),
+                "bg": sc_cpu.bg.pin_memory(), "gt_color": (torch.rand(3, H, W) * 255).to(torch.uint8).pin_memory()}
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+        leaves = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+        copy_stream = torch.cuda.Stream(device=dev)
+        r0, r1 = min(slab[0] * 16, H), min(slab[1] * 16, H)
 
-    def step_e2e():
-        for k in ("view", "proj", "campos", "bg"):                 # camera: needed by forward, current stream
-            dbuf[k].copy_(host[k], non_blocking=True)
-        copy_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(copy_stream):                        # ground truth: needed by the loss only -> overlaps forward
-            dbuf["gt_color"].copy_(host["gt_color"], non_blocking=True)
-        for t in leaves.values():
-            t.grad = None
-        means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
-        if a.impl == "ours":
-            st = dgr.GaussianRasterizationSettings(H, W, sc.tanfovx, sc.tanfovy, 0.0, dbuf["bg"], 1.0, dbuf["view"], dbuf["proj"], 3, dbuf["campos"],
-                                                   False, depth, coord, False)
-            rast = multigpu.ShardedGaussianRasterizer(st, rank=rank, world_size=world) if multi else dgr.GaussianRasterizer(st)
-            color, radii, co, mco, dep, mdep, alpha, normal = rast(leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"],
-                                                                    scales=leaves["scales"], rotations=leaves["rotations"])
-        else:
-            scd = {"bg": dbuf["bg"], "view": dbuf["view"], "proj": dbuf["proj"], "campos": dbuf["campos"], "tanx": sc.tanfovx, "tany": sc.tanfovy,
-                   "H": H, "W": W}
-            color, radii, co, mco, dep, mdep, alpha, normal = _RefFunction.apply(C, scd, coord, depth, 0.0, leaves["means3D"], means2D, leaves["shs"],
-                                                                                 leaves["opacities"], leaves["scales"], leaves["rotations"])
-        torch.cuda.current_stream().wait_stream(copy_stream)
-        sl = slice(r0, r1)
-        # photometric L1 against the 8-bit ground truth + small regularisers that keep the depth / normal / alpha gradient
-        # paths live (stand-ins for train.py's depth-normal consistency terms, which also need no ground truth)
-        loss = (color[:, sl] - dbuf["gt_color"][:, sl].float() * (1.0 / 255.0)).abs().mean() + 0.05 * dep[:, sl].mean() + \
-            0.05 * (1 - normal[2, sl]).mean() + 0.01 * alpha[:, sl].mean()
-        loss.backward()
-        return float(loss.item())                                   # D2H read of the step's result
+        def step_e2e():
+            for k in ("view", "proj", "campos", "bg"):                 # camera: needed by forward, current stream
+                dbuf[k].copy_(host[k], non_blocking=True)
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):                        # ground truth: needed by the loss only -> overlaps forward
+                dbuf["gt_color"].copy_(host["gt_color"], non_blocking=True)
+            for t in leaves.values():
+                t.grad = None
+            means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+            if ours:
+                st = dgr.GaussianRasterizationSettings(H, W, sc.tanfovx, sc.tanfovy, 0.0, dbuf["bg"], 1.0, dbuf["view"], dbuf["proj"], 3, dbuf["campos"],
+                                                       False, depth, coord, False)
+                rast = multigpu.ShardedGaussianRasterizer(st, rank=rank, world_size=world, exchange=exchange) if multi else dgr.GaussianRasterizer(st)
+                color, radii, co, mco, dep, mdep, alpha, normal = rast(leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"],
+                                                                        scales=leaves["scales"], rotations=leaves["rotations"])
+            else:
+                scd = {"bg": dbuf["bg"], "view": dbuf["view"], "proj": dbuf["proj"], "campos": dbuf["campos"], "tanx": sc.tanfovx, "tany": sc.tanfovy,
+                       "H": H, "W": W}
+                color, radii, co, mco, dep, mdep, alpha, normal = _RefFunction.apply(C, scd, coord, depth, 0.0, leaves["means3D"], means2D, leaves["shs"],
+                                                                                     leaves["opacities"], leaves["scales"], leaves["rotations"])
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            sl = slice(r0, r1)
+            # photometric L1 against the 8-bit ground truth + small regularisers that keep the depth / normal / alpha gradient
+            # paths live (stand-ins for train.py's depth-normal consistency terms, which also need no ground truth)
+            loss = (color[:, sl] - dbuf["gt_color"][:, sl].float() * (1.0 / 255.0)).abs().mean() + 0.01 * alpha[:, sl].mean()
+            if depth:
+                loss = loss + 0.05 * dep[:, sl].mean()
+            if coord:
+                loss = loss + 0.05 * co[2, sl].mean()
+            if depth or coord:
+                loss = loss + 0.05 * (1 - normal[2, sl]).mean()
+            loss.backward()
+            return float(loss.item())                                   # D2H read of the step's result
 
-    for _ in range(a.warmup):
-        step_e2e()
-    ms_e2e, _ = timed(step_e2e, a.steps)
-    e2e_value = W * H / (ms_e2e / a.steps * 1e-3) / 1e6
+        for _ in range(a.warmup):
+            step_e2e()
+        t_e2e, _ = measure(step_e2e)
+        e2e_value = W * H / (t_e2e["ms"] * 1e-3) / 1e6
+    clocks = clk.summary() if clk is not None else {}
 
-    # ---- per-stage device times (second pass, events recorded by the library on the launching stream) ----
-    roofline, stages = None, None
-    if a.impl == "ours" and hasattr(C, "stage_timing"):
+    # ---- per-stage device times (separate pass, events recorded by the library on the launching stream) ----
+    roofline = roofline_issue = stages = step_hbm = None
+    if ours and hasattr(C, "stage_timing"):
         C.stage_timing(True)
-        for _ in range(a.steps):
+        for _ in range(max(a.steps, 20)):
             step_resident()
         torch.cuda.synchronize()
         stages = C.stage_times()          # {name: (total_ms, launches)}
         C.stage_timing(False)
-        Pv = int((last_radii(C, sc, coord, depth) > 0).sum().item()) if not multi else None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        tot, n = stages.get("render_backward", (0.0, 0))
-        if n and Pv is not None:
-            tiles = ((W + 15) // 16) * grid_y
-            # R*(A_v+4) + N*I_v + 8*T + 4*G_v*Pv   (depth variant: A=60, I=68, G=16; coord: 84/92/22; both: 96/104/25)
-            A, I, G = {(False, False): (36, 28, 10), (False, True): (60, 68, 16), (True, False): (84, 92, 22), (True, True): (96, 104, 25)}[(coord, depth)]
-            alg = R * (A + 4) + W * H * I + 8 * tiles + 4 * G * Pv
-            dur = tot / n * 1e-3
-            traffic = None
-            try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/)
-                prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_render_backward_C2.json")))
-                if a.config == "C2":
-                    traffic = (float(prof["dram__bytes_read.sum"]["value"]) + float(prof["dram__bytes_write.sum"]["value"])) * 1e6
-            except Exception:
-                pass
-            roofline = {"kernel": "render_backward_kernel", "bound": "hbm", "achieved": alg / dur / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": alg / dur / 1e9 / peak, "traffic": traffic, "algorithmic_bytes": alg, "avg_launch_ms": tot / n,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                        "note": "issue-bound, not HBM-bound: ncu shows 80% issue-slot utilisation, 0.19 GB DRAM traffic (records are L2-resident); see DESIGN.md section 4"}
+        peak_source = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        if not multi:
+            Pv = int((rawapi.forward(C, sc, coord, depth)["radii"] > 0).sum().item())
+            alg = algorithmic_bytes(P, Pv, R, W * H, tiles, 16, coord, depth)
+            stage_of = {"preprocess_forward": "preprocess_forward", "scan": "binning", "binning_sort": "binning", "render_forward": "render_forward",
+                        "render_backward": "render_backward", "preprocess_backward": "preprocess_backward"}
+            tot, n = stages.get("render_backward", (0.0, 0))
+            if n:
+                dur = tot / n * 1e-3
+                prof, prof_name = None, f"profiles/r02_ncu_render_backward_{a.config}.json"
+                try:
+                    prof = json.load(open(os.path.join(ROOT, prof_name)))
+                except Exception:
+                    pass
+                traffic = None
+                if prof:
+                    traffic = float(prof["dram__bytes_read.sum"]["value"]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(prof["dram__bytes_read.sum"].get("unit", "Mbyte"), 1e6) + \
+                        float(prof["dram__bytes_write.sum"]["value"]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(prof["dram__bytes_write.sum"].get("unit", "Mbyte"), 1e6)
+                roofline = {"kernel": "render_backward_kernel", "bound": "hbm", "achieved": alg["render_backward"] / dur / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": alg["render_backward"] / dur / 1e9 / peak, "traffic": traffic,
+                            "traffic_source": (f"REPLAYED from {prof_name} (one `ncu --set full` capture of this kernel on this config), not measured in this run"
+                                               if traffic is not None else None),
+                            "algorithmic_bytes": alg["render_backward"], "avg_launch_ms": tot / n, "peak_source": peak_source,
+                            "note": "this kernel is warp-instruction-issue bound, not HBM bound (records are L2-resident); see roofline_issue and DESIGN.md section 4"}
+                if prof and "smsp__inst_executed.sum" in prof:
+                    inst = float(prof["smsp__inst_executed.sum"]["value"])
+                    clk_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                    floor = inst / (SM_COUNT * 4 * clk_hz)
+                    roofline_issue = {"kernel": "render_backward_kernel", "bound": "warp-instruction issue (4 schedulers/SM, 1 inst/clk each)",
+                                      "warp_instructions": inst, "warp_instructions_source": f"REPLAYED from {prof_name}",
+                                      "sm_clock_mhz": clk_hz / 1e6, "floor_ms": floor * 1e3, "avg_launch_ms": tot / n, "frac": floor / dur}
+            step_alg = sum(alg.values())
+            step_hbm = {"algorithmic_bytes": step_alg, "achieved": step_alg / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s", "peak": peak, "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak,
+                        "per_stage": {}}
+            agg = {}
+            for k, (t_ms, n) in stages.items():
+                if n:
+                    agg[stage_of[k]] = agg.get(stage_of[k], 0.0) + t_ms / n
+            for k, t_ms in agg.items():
+                step_hbm["per_stage"][k] = {"ms": t_ms, "algorithmic_bytes": alg[k], "GBps": alg[k] / (t_ms * 1e-3) / 1e9, "frac": alg[k] / (t_ms * 1e-3) / 1e9 / peak}
 
     if rank == 0:
         line = {
@@ -370,30 +456,32 @@ def main():
             "impl": a.impl,
             "config": {"workload": f"{a.config}: {P} random-init Gaussians (SURVEY app. C seed 1234), {W}x{H}, SH deg 3, "
                                    f"require_depth={depth} require_coord={coord}, fwd+bwd at the _C boundary, num_rendered={R if not multi else 'per-slab'}",
-                       "parallelism": f"tile-row slabs x{world}" if multi else "single GPU",
-                       "l2": "per-step working set (192 MB SH + 248 MB SH grads + 64 MB records + sort buffers) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps,
+                       "parallelism": (f"tile-row slabs x{world}, gradient-row exchange: {exchange.mode}" if multi else "single GPU"),
+                       "l2": "per-step working set (192 MB SH + 248 MB SH grads + 64 MB records + sort buffers) exceeds the 126 MB L2; no explicit flush",
+                       "protocol": f"median of {t_res['iterations']} per-iteration CUDA-event times ({t_res['windows']} windows of {a.steps} steps, barrier+synchronize around each window, max over ranks per iteration)"},
+            "timing": t_res,
+            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": t_e2e["ms"], "timing": t_e2e,
                     "api": "GaussianRasterizer autograd module (what render() calls) + L1 vs 8-bit GT image + depth/normal/alpha regularisers; camera + GT image H2D from pinned memory every step (GT on a side stream), loss.item() D2H"},
-            "gpu_launches": launches, "clocks": clk.summary(),
+            "gpu_launches": launches, "clocks": clocks,
         }
         if stages:
             line["stage_ms"] = {k: v[0] / max(v[1], 1) for k, v in stages.items()}
         if roofline:
             line["roofline"] = roofline
+        if roofline_issue:
+            line["roofline_issue"] = roofline_issue
+        if step_hbm:
+            line["step_hbm"] = step_hbm
         if a.impl == "reference":
             line["cpu_baseline"] = {"value": value, "unit": "Mpix/s", "cores": 0, "kind": "reference",
                                     "sample": "reference CUDA rasterizer (oracle/_ref, sm_100a build of /root/reference) on 1xB200; the reference has no CPU rasterizer"}
-            line["e2e"] = {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+            line["e2e"] = {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": t_e2e["ms"], "timing": t_e2e}
         elif not a.no_cpu_baseline and not multi:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if multi:
+        exchange.close()
         dist.destroy_process_group()
-
-
-def last_radii(C, sc, coord, depth):
-    from rade_gs_b200 import rawapi
-    return rawapi.forward(C, sc, coord, depth)["radii"]
 
 
 if __name__ == "__main__":

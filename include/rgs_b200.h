@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RGS_ABI_VERSION 2
+#define RGS_ABI_VERSION 3
 
 typedef enum rgs_status {
 	RGS_OK = 0,
@@ -178,6 +178,33 @@ int32_t rgs_backward_preprocess(const rgs_camera* cam, const rgs_gaussians* g, c
 int32_t rgs_backward(const rgs_camera* cam, const rgs_gaussians* g, const rgs_backward_in* in,
                      const rgs_backward_out* out, rgs_resize_fn grad_scratch, void* grad_scratch_user,
                      void* cuda_stream);
+
+/* ---- multi-GPU: device-side exchange of the accumulator rows over peer memory (ABI 3; DESIGN.md "Multi-GPU") ----
+ * One process per GPU, rank r renders the tile rows of its slab (rgs_camera.tile_row_begin/end).  The north star's
+ * "all-reduce of the per-Gaussian gradients after backward" is done by the library itself over NVLink instead of by a
+ * host-driven collective: each rank creates one exchange object (a device allocation exported with cudaIpcGetMemHandle),
+ * the caller gathers the 64-byte handles of all ranks with whatever transport it has (torch.distributed in the product)
+ * and connects; after that
+ *     rgs_backward_render_exchange  = stage 1 into a persistent local accumulator + push of the touched rows to their
+ *                                     owner rank (vector reductions into peer memory) + barrier + spread of the summed
+ *                                     rows to every rank + barrier (all on the given stream, no host synchronisation)
+ *     rgs_exchange_result           = the summed rows [capacity, row_floats] to hand to rgs_backward_preprocess
+ * All ranks must make the same sequence of calls with the same P.  The result is bit-identical on every rank.
+ * The reference is single-GPU and has no equivalent; the sum reproduced is backward.cu:878-1013's atomic accumulation. */
+typedef struct rgs_exchange rgs_exchange;
+#define RGS_IPC_HANDLE_BYTES 64
+int32_t rgs_exchange_create(int32_t rank, int32_t world, int64_t capacity_rows, int32_t row_floats, rgs_exchange** out,
+                            void* ipc_handle /* host, RGS_IPC_HANDLE_BYTES */);
+int32_t rgs_exchange_connect(rgs_exchange* ex, const void* all_handles /* host, world * RGS_IPC_HANDLE_BYTES, rank-major */);
+int32_t rgs_exchange_destroy(rgs_exchange* ex);
+float* rgs_exchange_accumulator(rgs_exchange* ex);     /* persistent local accumulator (all-zero between steps) */
+const float* rgs_exchange_result(rgs_exchange* ex);    /* summed rows, valid after rgs_backward_render_exchange on the same stream */
+/* push + barrier + spread + barrier for an accumulator already filled by stage 1 (tiles_touched: this call's per-splat tile
+ * counts inside the slab, radii: forward's radii) */
+int32_t rgs_exchange_rows(rgs_exchange* ex, int32_t P, const uint32_t* tiles_touched, const int32_t* radii, void* cuda_stream);
+int32_t rgs_backward_render_exchange(const rgs_camera* cam, const rgs_gaussians* g, const rgs_backward_in* in, rgs_exchange* ex,
+                                     void* cuda_stream);
+const char* rgs_exchange_last_error(void);
 
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:18-23, rasterizer_impl.cu:176-188). */
 int32_t rgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -22,8 +22,8 @@ static thread_local std::string t_error;
 
 // ---- optional per-stage device timing (bench.py's roofline leg): cudaEvents recorded on the launching stream
 // around each stage, read back by rgs_stage_times() after a synchronize.  Off by default: zero overhead.
-enum Stage { ST_PREPROCESS, ST_SCAN, ST_BINNING, ST_RENDER_FWD, ST_RENDER_BWD, ST_PREPROCESS_BWD, ST_COUNT };
-static const char* kStageNames[ST_COUNT] = {"preprocess_forward", "scan", "binning_sort", "render_forward", "render_backward", "preprocess_backward"};
+enum Stage { ST_PREPROCESS, ST_SCAN, ST_BINNING, ST_RENDER_FWD, ST_RENDER_BWD, ST_PREPROCESS_BWD, ST_EXCHANGE, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"preprocess_forward", "scan", "binning_sort", "render_forward", "render_backward", "preprocess_backward", "gradient_exchange"};
 struct StageRec { int stage; cudaEvent_t a, b; };
 static std::mutex g_stage_mu;
 static std::vector<StageRec> g_stage_pending;
@@ -130,6 +130,8 @@ static int make_params(const rgs_camera* cam, const rgs_gaussians* g, FwdParams&
 		return fail(RGS_E_INVALID, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
 	if (has_sh && (cam->sh_degree < 0 || cam->sh_degree > 3 || (cam->sh_degree + 1) * (cam->sh_degree + 1) > cam->sh_coeffs))
 		return fail(RGS_E_INVALID, "sh_degree does not fit the stored SH coefficients");
+	if (has_sh && cam->sh_coeffs > 16)
+		return fail(RGS_E_INVALID, "at most 16 SH coefficients per Gaussian (degree 3) are supported");  // the SH kernels stage rows of <= 16 x 3 floats
 	p.P = g->P;
 	p.D = cam->sh_degree;
 	p.M = has_sh ? cam->sh_coeffs : 0;
@@ -243,6 +245,10 @@ static int64_t forward_to_binning(const rgs_camera* cam, const FwdParams& p, int
 	char* bin_ptr = bufs->binning(bufs->binning_user, bin_bytes);
 	if (!bin_ptr) return fail(RGS_E_ALLOC, "binning buffer callback returned NULL");
 	b = carve_bin(bin_ptr, (size_t)R, tiles, sort_bytes, nullptr);
+	// forward-render writes a ballot word only for the chunks a warp actually tested; backward masks every position at or
+	// behind the warp's last contributor, so the unwritten words never matter -- zero them anyway (<= R bytes) so that no
+	// consumer (debug views, initcheck) ever sees memory the library did not write
+	if (R > 0) RGS_CUDA_TRY(cudaMemsetAsync(b.hitmask, 0, hitmask_words((size_t)R, tiles) * sizeof(uint32_t), s));
 
 	if (P == 0) {
 		RGS_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, (size_t)tiles * sizeof(uint2), s));
@@ -366,6 +372,29 @@ int32_t rgs_backward_render(const rgs_camera* cam, const rgs_gaussians* gs, cons
 	                 in->dL_dout_alpha, in->dL_dout_normal, in->out_alpha, in->out_normal};
 	{ StageScope sc(ST_RENDER_BWD, s); launch_render_backward(p, g, b, img, gin, grad_accum, s); }
 	return debug_sync(cam, s, "backward render");
+}
+
+int32_t rgs_backward_render_exchange(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, rgs_exchange* ex, void* cuda_stream) {
+	FwdParams p;
+	GeomView g;
+	BinView b;
+	ImgView img;
+	int rc = backward_views(cam, gs, in, p, g, b, img);
+	if (rc != RGS_OK) return rc;
+	if (p.P == 0) return RGS_OK;
+	float* acc = rgs_exchange_accumulator(ex);
+	if (!acc) return fail(RGS_E_INVALID, "null exchange");
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	RenderGradIn gin{in->dL_dout_color, in->dL_dout_coord, in->dL_dout_mcoord, in->dL_dout_depth, in->dL_dout_mdepth,
+	                 in->dL_dout_alpha, in->dL_dout_normal, in->out_alpha, in->out_normal};
+	{ StageScope sc(ST_RENDER_BWD, s); launch_render_backward(p, g, b, img, gin, acc, s, /*zero_first=*/false); }
+	if ((rc = debug_sync(cam, s, "backward render")) != RGS_OK) return rc;
+	{
+		StageScope sc(ST_EXCHANGE, s);
+		rc = rgs_exchange_rows(ex, p.P, g.tiles_touched, in->radii, cuda_stream);
+	}
+	if (rc != RGS_OK) return fail(rc, rgs_exchange_last_error());
+	return debug_sync(cam, s, "gradient exchange");
 }
 
 int32_t rgs_backward_preprocess(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, const float* grad_accum,

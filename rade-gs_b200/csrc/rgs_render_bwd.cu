@@ -368,9 +368,11 @@ static void launch_variant(const FwdParams& p, GeomView g, BinView b, ImgView im
 	count_launch();
 }
 
-void launch_render_backward(const FwdParams& p, GeomView g, BinView b, ImgView img, RenderGradIn gin, float* grad_accum, cudaStream_t s) {
-	cudaMemsetAsync(grad_accum, 0, (size_t)p.P * grad_floats(p.coord) * sizeof(float), s);
-	count_launch();
+void launch_render_backward(const FwdParams& p, GeomView g, BinView b, ImgView img, RenderGradIn gin, float* grad_accum, cudaStream_t s, bool zero_first) {
+	if (zero_first) {
+		cudaMemsetAsync(grad_accum, 0, (size_t)p.P * grad_floats(p.coord) * sizeof(float), s);
+		count_launch();
+	}
 	if (p.row_end <= p.row_begin) return;
 	if (p.coord && p.depth)
 		launch_variant<true, true>(p, g, b, img, gin, grad_accum, s);

@@ -32,9 +32,26 @@ torch::Tensor as_input(const torch::Tensor& t, const torch::Tensor& like, const 
 	return t.contiguous();
 }
 
+// Debug aid (`_C.set_poison(byte)`, tests only): every scratch buffer and every empty()-allocated output is filled with
+// `byte` before the kernels run, so a read of memory the kernels did not write themselves changes the result instead of
+// silently depending on what the caching allocator handed out (fresh pages in one process, stale data in another).
+int g_poison = -1;
+
+void poison(const torch::Tensor& t) {
+	if (g_poison >= 0 && t.defined() && t.numel() > 0 && t.is_cuda())
+		cudaMemsetAsync(t.data_ptr(), g_poison, t.nbytes(), at::cuda::getCurrentCUDAStream(t.device().index()).stream());
+}
+
+torch::Tensor new_empty(at::IntArrayRef shape, const torch::TensorOptions& o) {
+	torch::Tensor t = torch::empty(shape, o);
+	poison(t);
+	return t;
+}
+
 char* resize_cb(void* user, size_t bytes) {
 	auto* t = reinterpret_cast<torch::Tensor*>(user);
 	t->resize_({(long long)bytes});
+	poison(*t);
 	return reinterpret_cast<char*>(t->data_ptr());
 }
 
@@ -138,10 +155,10 @@ FwdResult forward_impl(const torch::Tensor& background, const torch::Tensor& mea
 	const int grid_y = (H + 15) / 16;
 	const bool whole = (row_begin == 0 && (row_end < 0 || row_end == grid_y));
 	const bool fill = (P == 0) || !whole;  // P == 0: the reference returns all-zero maps (rasterize_points.cu:90)
-	auto img = [&](int ch) { return fill ? torch::zeros({ch, H, W}, float_opts) : torch::empty({ch, H, W}, float_opts); };
+	auto img = [&](int ch) { return fill ? torch::zeros({ch, H, W}, float_opts) : new_empty({ch, H, W}, float_opts); };
 	torch::Tensor out_color = img(3), out_depth = img(1), out_mdepth = img(1), out_coord = img(3), out_mcoord = img(3), out_alpha = img(1),
 	              out_normal = img(3);
-	torch::Tensor radii = P == 0 ? torch::zeros({P}, int_opts) : torch::empty({P}, int_opts);
+	torch::Tensor radii = P == 0 ? torch::zeros({P}, int_opts) : new_empty({P}, int_opts);
 	torch::Tensor geomBuffer = torch::empty({0}, byte_opts), binningBuffer = torch::empty({0}, byte_opts), imgBuffer = torch::empty({0}, byte_opts);
 
 	int rendered = 0;
@@ -236,7 +253,7 @@ struct GradTensors {
 
 void alloc_grads(GradTensors& t, const torch::Tensor& means3D, int P, int M, bool split_sh = false) {
 	auto o = means3D.options();
-	auto mk = [&](std::initializer_list<int64_t> shape) { return P == 0 ? torch::zeros(shape, o) : torch::empty(shape, o); };
+	auto mk = [&](std::initializer_list<int64_t> shape) { return P == 0 ? torch::zeros(shape, o) : new_empty(shape, o); };
 	t.means3D = mk({P, 3});
 	t.means2D = mk({P, 3});
 	t.colors = mk({P, 3});
@@ -323,12 +340,12 @@ IntegrateGaussiansToPointsCUDA(const torch::Tensor& background, const torch::Ten
 	auto float_opts = means3D.options().dtype(torch::kFloat32);
 	auto byte_opts = means3D.options().dtype(torch::kByte);
 	const bool run = P != 0 && PN != 0;  // rasterize_points.cu:341: otherwise the fill values below are returned
-	torch::Tensor out_color = run ? torch::empty({9, H, W}, float_opts) : torch::zeros({9, H, W}, float_opts);
-	torch::Tensor radii = run ? torch::empty({P}, int_opts) : torch::zeros({P}, int_opts);
-	torch::Tensor out_alpha_integrated = run ? torch::empty({PN}, float_opts) : torch::full({PN}, 1.0, float_opts);
-	torch::Tensor out_color_integrated = run ? torch::empty({PN, 3}, float_opts) : torch::zeros({PN, 3}, float_opts);
-	torch::Tensor out_coordinate2d = run ? torch::empty({PN, 2}, float_opts) : torch::zeros({PN, 2}, float_opts);
-	torch::Tensor out_sdf = run ? torch::empty({PN}, float_opts) : torch::full({PN}, -1000.0, float_opts);
+	torch::Tensor out_color = run ? new_empty({9, H, W}, float_opts) : torch::zeros({9, H, W}, float_opts);
+	torch::Tensor radii = run ? new_empty({P}, int_opts) : torch::zeros({P}, int_opts);
+	torch::Tensor out_alpha_integrated = run ? new_empty({PN}, float_opts) : torch::full({PN}, 1.0, float_opts);
+	torch::Tensor out_color_integrated = run ? new_empty({PN, 3}, float_opts) : torch::zeros({PN, 3}, float_opts);
+	torch::Tensor out_coordinate2d = run ? new_empty({PN, 2}, float_opts) : torch::zeros({PN, 2}, float_opts);
+	torch::Tensor out_sdf = run ? new_empty({PN}, float_opts) : torch::full({PN}, -1000.0, float_opts);
 	torch::Tensor geomBuffer = torch::empty({0}, byte_opts), binningBuffer = torch::empty({0}, byte_opts), imgBuffer = torch::empty({0}, byte_opts),
 	              pointBuffer = torch::empty({0}, byte_opts);
 	int rendered = 0;
@@ -345,7 +362,7 @@ IntegrateGaussiansToPointsCUDA(const torch::Tensor& background, const torch::Ten
 		                    out_color_integrated.data_ptr<float>(), out_coordinate2d.data_ptr<float>(), out_sdf.data_ptr<float>(), radii.data_ptr<int>()};
 		rgs_buffers bufs{resize_cb, &geomBuffer, resize_cb, &binningBuffer, resize_cb, &imgBuffer};
 		int32_t overflowed = 0;
-		const int64_t rc = rgs_integrate(&ch.cam, &gh.g, &io, &bufs, resize_cb, &pointBuffer, debug ? &overflowed : nullptr,
+		const int64_t rc = rgs_integrate(&ch.cam, &gh.g, &io, &bufs, resize_cb, &pointBuffer, &overflowed,  // always read: 4 bytes on a call that synchronises anyway
 		                                 at::cuda::getCurrentCUDAStream().stream());
 		check(rc);
 		rendered = (int)rc;
@@ -384,7 +401,7 @@ torch::Tensor BackwardRenderCUDA(const torch::Tensor& background, const torch::T
 	const c10::cuda::CUDAGuard guard(means3D.device());
 	const int P = means3D.size(0);
 	const int GS = rgs_grad_stride(require_coord, require_depth);
-	torch::Tensor acc = P == 0 ? torch::zeros({P, GS}, means3D.options()) : torch::empty({P, GS}, means3D.options());
+	torch::Tensor acc = P == 0 ? torch::zeros({P, GS}, means3D.options()) : new_empty({P, GS}, means3D.options());
 	if (P != 0) {
 		BackwardCtx c;
 		fill_backward(c, background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
@@ -394,6 +411,55 @@ torch::Tensor BackwardRenderCUDA(const torch::Tensor& background, const torch::T
 		check(rgs_backward_render(&c.ch.cam, &c.gh.g, &c.in, acc.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
 	}
 	return acc;
+}
+
+// ---- device-side exchange of the accumulator rows over peer memory (rgs_exchange_*) ----
+// The exchange object is handed to Python as an integer handle; the IPC handle as a CPU uint8 tensor [64] the caller
+// all-gathers with torch.distributed before `exchange_connect`.
+std::tuple<int64_t, torch::Tensor> ExchangeCreate(const int rank, const int world, const int64_t capacity_rows, const int row_floats, const int device) {
+	const c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, device));
+	rgs_exchange* ex = nullptr;
+	torch::Tensor handle = torch::zeros({RGS_IPC_HANDLE_BYTES}, torch::kUInt8);
+	if (rgs_exchange_create(rank, world, capacity_rows, row_floats, &ex, handle.data_ptr()) != RGS_OK) throw std::runtime_error(rgs_exchange_last_error());
+	return std::make_tuple((int64_t)reinterpret_cast<intptr_t>(ex), handle);
+}
+
+void ExchangeConnect(const int64_t ex, const torch::Tensor& all_handles, const int device) {
+	const c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, device));
+	torch::Tensor h = all_handles.to(torch::kCPU).contiguous();
+	TORCH_CHECK(h.scalar_type() == torch::kUInt8 && h.numel() % RGS_IPC_HANDLE_BYTES == 0, "handles must be a uint8 tensor [world, 64]");
+	if (rgs_exchange_connect(reinterpret_cast<rgs_exchange*>(ex), h.data_ptr()) != RGS_OK) throw std::runtime_error(rgs_exchange_last_error());
+}
+
+void ExchangeDestroy(const int64_t ex) { rgs_exchange_destroy(reinterpret_cast<rgs_exchange*>(ex)); }
+
+// stage 1 + exchange: same arguments as BackwardRenderCUDA after the handle; returns the SUMMED rows [P, stride] (a view
+// of the exchange's result buffer: valid until the next call on this exchange)
+torch::Tensor BackwardRenderExchangeCUDA(const int64_t ex, const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                                         const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                         const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                         const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const float kernel_size,
+                                         const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_coord, const torch::Tensor& dL_dout_mcoord,
+                                         const torch::Tensor& dL_dout_depth, const torch::Tensor& dL_dout_mdepth, const torch::Tensor& dL_dout_alpha,
+                                         const torch::Tensor& dL_dout_normal, const torch::Tensor& normalmap, const torch::Tensor& sh, const int degree,
+                                         const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
+                                         const torch::Tensor& imageBuffer, const torch::Tensor& alphas, const bool require_coord,
+                                         const bool require_depth, const bool debug, const int tile_row_begin, const int tile_row_end) {
+	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor: this rasterizer has no CPU path");
+	const c10::cuda::CUDAGuard guard(means3D.device());
+	const int P = means3D.size(0);
+	const int GS = rgs_grad_stride(require_coord, require_depth);
+	rgs_exchange* x = reinterpret_cast<rgs_exchange*>(ex);
+	TORCH_CHECK(x != nullptr, "null exchange handle");
+	if (P != 0) {
+		BackwardCtx c;
+		fill_backward(c, background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+		              tan_fovy, kernel_size, dL_dout_color, dL_dout_coord, dL_dout_mcoord, dL_dout_depth, dL_dout_mdepth, dL_dout_alpha,
+		              dL_dout_normal, normalmap, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, alphas, require_coord, require_depth,
+		              debug, tile_row_begin, tile_row_end);
+		check(rgs_backward_render_exchange(&c.ch.cam, &c.gh.g, &c.in, x, at::cuda::getCurrentCUDAStream().stream()));
+	}
+	return torch::from_blob(const_cast<float*>(rgs_exchange_result(x)), {P, GS}, means3D.options().dtype(torch::kFloat32));
 }
 
 // stage 2: accumulator (after the cross-rank sum) -> the reference's 8-tuple of parameter gradients
@@ -485,7 +551,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> ActivateForward(const to
 	torch::Tensor s = as_input(raw_scaling, raw_scaling, "raw_scaling"), o = as_input(raw_opacity, raw_scaling, "raw_opacity"),
 	              r = as_input(raw_rotation, raw_scaling, "raw_rotation"), f = as_input(filter_3D, raw_scaling, "filter_3D");
 	TORCH_CHECK(s.numel() == 3 * (int64_t)P && o.numel() == P && r.numel() == 4 * (int64_t)P && f.numel() == P, "activate: shapes must be [P,3] [P,1] [P,4] [P,1]");
-	torch::Tensor scales = torch::empty({P, 3}, s.options()), opacity = torch::empty({P, 1}, s.options()), rot = torch::empty({P, 4}, s.options());
+	torch::Tensor scales = new_empty({P, 3}, s.options()), opacity = new_empty({P, 1}, s.options()), rot = new_empty({P, 4}, s.options());
 	if (P)
 		check(rgs_activate_forward(P, s.data_ptr<float>(), o.data_ptr<float>(), r.data_ptr<float>(), f.data_ptr<float>(), scales.data_ptr<float>(),
 		                           opacity.data_ptr<float>(), rot.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
@@ -503,7 +569,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> ActivateBackward(const t
 	              gs = as_input(g_scales, raw_scaling, "g_scales"), go = as_input(g_opacity, raw_scaling, "g_opacity"),
 	              gr = as_input(g_rotations, raw_scaling, "g_rotations");
 	TORCH_CHECK(gs.numel() == 3 * (int64_t)P && go.numel() == P && gr.numel() == 4 * (int64_t)P, "activate backward: gradient shapes must be [P,3] [P,1] [P,4]");
-	torch::Tensor ds = torch::empty({P, 3}, s.options()), dop = torch::empty({P, 1}, s.options()), dr = torch::empty({P, 4}, s.options());
+	torch::Tensor ds = new_empty({P, 3}, s.options()), dop = new_empty({P, 1}, s.options()), dr = new_empty({P, 4}, s.options());
 	if (P)
 		check(rgs_activate_backward(P, s.data_ptr<float>(), o.data_ptr<float>(), r.data_ptr<float>(), f.data_ptr<float>(), gs.data_ptr<float>(),
 		                            go.data_ptr<float>(), gr.data_ptr<float>(), ds.data_ptr<float>(), dop.data_ptr<float>(), dr.data_ptr<float>(),
@@ -537,7 +603,7 @@ std::tuple<torch::Tensor, torch::Tensor> Compute3DFilter(const torch::Tensor& xy
 	const int P = xyz.size(0);
 	TORCH_CHECK(c.numel() % 16 == 0, "camera table must be [n_cams,16]");
 	const int n = (int)(c.numel() / 16);
-	torch::Tensor out = torch::empty({P, 1}, x.options()), mx = torch::zeros({1}, x.options());
+	torch::Tensor out = new_empty({P, 1}, x.options()), mx = torch::zeros({1}, x.options());
 	if (P)
 		check(rgs_compute_3d_filter(P, x.data_ptr<float>(), n, n ? c.data_ptr<float>() : nullptr, (float)focal_length, out.data_ptr<float>(),
 		                            mx.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
@@ -561,8 +627,8 @@ std::tuple<torch::Tensor, torch::Tensor> SsimL1Forward(const torch::Tensor& img,
 	const c10::cuda::CUDAGuard guard(a.device());
 	const int H = a.size(-2), W = a.size(-1);
 	const int planes = (int)(a.numel() / ((int64_t)H * W));
-	torch::Tensor sums = torch::empty({2}, a.options().dtype(torch::kFloat64));
-	torch::Tensor dmaps = need_grad ? torch::empty({3, planes, H, W}, a.options()) : torch::empty({0}, a.options());
+	torch::Tensor sums = new_empty({2}, a.options().dtype(torch::kFloat64));
+	torch::Tensor dmaps = need_grad ? new_empty({3, planes, H, W}, a.options()) : torch::empty({0}, a.options());
 	check(rgs_ssim_l1_forward(planes, H, W, a.data_ptr<float>(), b.data_ptr<float>(), need_grad ? dmaps.data_ptr<float>() : nullptr,
 	                          sums.data_ptr<double>(), at::cuda::getCurrentCUDAStream().stream()));
 	return std::make_tuple(sums, dmaps);
@@ -582,7 +648,7 @@ torch::Tensor SsimL1Backward(const torch::Tensor& img, const torch::Tensor& gt, 
 		up = image_input(upstream, img, "upstream gradient");
 		up_ptr = up.data_ptr<float>();
 	}
-	torch::Tensor out = torch::empty_like(a);
+	torch::Tensor out = new_empty(a.sizes(), a.options());
 	check(rgs_ssim_l1_backward(planes, H, W, a.data_ptr<float>(), b.data_ptr<float>(), d.data_ptr<float>(), (float)w_ssim, (float)w_l1, up_ptr,
 	                           out.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
 	return out.view(img.sizes());
@@ -602,8 +668,8 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> NormalCon
 	const int H = n.size(1), W = n.size(2);
 	const int64_t want = (from_depth ? 1 : 3) * (int64_t)H * W;
 	TORCH_CHECK(e.numel() == want && m.numel() == want, from_depth ? "depth maps must be [1,H,W]" : "coordinate maps must be [3,H,W]");
-	torch::Tensor loss = torch::empty({1}, n.options().dtype(torch::kFloat64));
-	torch::Tensor dn = torch::empty_like(n), de = torch::empty_like(e), dm = torch::empty_like(m);
+	torch::Tensor loss = new_empty({1}, n.options().dtype(torch::kFloat64));
+	torch::Tensor dn = new_empty(n.sizes(), n.options()), de = new_empty(e.sizes(), e.options()), dm = new_empty(m.sizes(), m.options());
 	check(rgs_normal_consistency(H, W, from_depth ? 1 : 0, (float)inv_fx, (float)inv_fy, (float)cx, (float)cy, n.data_ptr<float>(), e.data_ptr<float>(),
 	                             m.data_ptr<float>(), (float)w_expected, (float)w_median, loss.data_ptr<double>(), dn.data_ptr<float>(),
 	                             de.data_ptr<float>(), dm.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
@@ -621,6 +687,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("rasterize_gaussians_slab", &RasterizeGaussiansSlabCUDA);
 	m.def("rasterize_gaussians_backward_render", &BackwardRenderCUDA);
 	m.def("rasterize_gaussians_backward_preprocess", &BackwardPreprocessCUDA);
+	m.def("exchange_create", &ExchangeCreate);
+	m.def("exchange_connect", &ExchangeConnect);
+	m.def("exchange_destroy", &ExchangeDestroy);
+	m.def("rasterize_gaussians_backward_render_exchange", &BackwardRenderExchangeCUDA);
 	m.def("rasterize_gaussians_split_sh", &RasterizeGaussiansSplitShCUDA);
 	m.def("rasterize_gaussians_backward_split_sh", &RasterizeGaussiansBackwardSplitShCUDA);
 	m.def("compute_3d_filter", &Compute3DFilter);
@@ -631,6 +701,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("activate_backward", &ActivateBackward);
 	m.def("densification_stats", &DensificationStats);
 	m.def("grad_stride", [](bool require_coord, bool require_depth) { return rgs_grad_stride(require_coord, require_depth); });
+	m.def("set_poison", [](int byte) { g_poison = byte; });
 	m.def("launch_count", []() { return rgs_launch_count(); });
 	m.def("abi_version", []() { return rgs_abi_version(); });
 	m.def("stage_timing", [](bool on) { rgs_stage_timing(on); });

@@ -115,6 +115,52 @@ def exchange_sum_(acc: torch.Tensor, group=None, mode: str | None = None) -> tor
     return acc
 
 
+class GradExchange:
+    """The one exchange step of the sharded backward: slab-local accumulator rows -> summed rows on every rank.
+
+    ``peer`` (default on CUDA with NCCL): the library's device-side exchange over peer memory (csrc/rgs_exchange.cu: touched
+    rows are reduced into their owner rank with vector reductions through NVLink, the sums are spread to every rank, two
+    flag barriers, no host synchronisation; bit-identical rows on all ranks).  torch.distributed is used ONCE, to all-gather
+    the 64-byte IPC handles.  ``dense`` (``RGS_GRAD_EXCHANGE=dense``, and the only mode off-GPU): stage 1 into a fresh tensor
+    + one NCCL / gloo all-reduce of the whole tensor.
+
+    All ranks must create the object collectively and call ``backward_render`` the same number of times with the same P.
+    """
+
+    def __init__(self, capacity_rows: int, row_floats: int, device, group=None, mode: str | None = None):
+        self.group, self.device = group, torch.device(device)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        mode = mode or os.environ.get("RGS_GRAD_EXCHANGE", "peer")
+        if self.world == 1 or self.device.type != "cuda":
+            mode = "dense"
+        self.mode, self.capacity, self.row_floats, self._ex = mode, int(capacity_rows), int(row_floats), None
+        if mode == "peer":
+            from diff_gaussian_rasterization import _C
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            self._ex, handle = _C.exchange_create(self.rank, self.world, self.capacity, self.row_floats, idx)
+            mine = handle.to(self.device)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine, group=group)
+            _C.exchange_connect(self._ex, torch.stack(gathered).cpu(), idx)
+            dist.barrier(group=group)   # nobody pushes before every rank has mapped every window
+
+    def backward_render(self, C, *stage1_args) -> torch.Tensor:
+        """stage 1 (`rasterize_gaussians_backward_render` arguments) + exchange -> summed accumulator rows [P, row_floats]."""
+        if self.mode == "peer":
+            return C.rasterize_gaussians_backward_render_exchange(self._ex, *stage1_args)
+        acc = C.rasterize_gaussians_backward_render(*stage1_args)
+        return exchange_sum_(acc, self.group, mode="dense")
+
+    def close(self):
+        if self._ex is not None:
+            from diff_gaussian_rasterization import _C
+            if dist.is_initialized():
+                dist.barrier(group=self.group)   # peers may still be reading / writing this rank's window
+            _C.exchange_destroy(self._ex)
+            self._ex = None
+
+
 def backward_two_stage(stage1_render: Callable[[], torch.Tensor], stage2_preprocess: Callable[[torch.Tensor], tuple], group=None):
     """slab-local scatter -> one exchange of the accumulator rows -> replicated parameter gradients."""
     acc = stage1_render()
@@ -127,7 +173,7 @@ class _ShardedRasterize(torch.autograd.Function):
     `_RasterizeGaussians` (reference: diff_gaussian_rasterization/__init__.py:44-169)."""
 
     @staticmethod
-    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, slab, group):
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, slab, group, exchange=None):
         from diff_gaussian_rasterization import _C
         s = raster_settings
         out = _C.rasterize_gaussians_slab(
@@ -135,7 +181,7 @@ class _ShardedRasterize(torch.autograd.Function):
             s.tanfovx, s.tanfovy, s.kernel_size, s.image_height, s.image_width, sh, s.sh_degree, s.campos, s.prefiltered,
             s.require_coord, s.require_depth, s.debug, slab[0], slab[1])
         num_rendered, color, coord, mcoord, alpha, normal, depth, mdepth, radii, geom, binning, img = out
-        ctx.s, ctx.slab, ctx.group, ctx.num_rendered = s, slab, group, num_rendered
+        ctx.s, ctx.slab, ctx.group, ctx.num_rendered, ctx.exchange = s, slab, group, num_rendered, exchange
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, normal, radii, sh, geom, binning, img, alpha, opacities)
         return color, radii, coord, mcoord, depth, mdepth, alpha, normal
 
@@ -145,12 +191,13 @@ class _ShardedRasterize(torch.autograd.Function):
         s = ctx.s
         colors_precomp, means3D, scales, rotations, cov3Ds_precomp, normal, radii, sh, geom, binning, img, alpha, opacities = ctx.saved_tensors
 
+        stage1_args = (s.bg, means3D, radii, colors_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp, s.viewmatrix, s.projmatrix,
+                       s.tanfovx, s.tanfovy, s.kernel_size, g_color, g_coord, g_mcoord, g_depth, g_mdepth, g_alpha, g_normal, normal, sh,
+                       s.sh_degree, s.campos, geom, ctx.num_rendered, binning, img, alpha, s.require_coord, s.require_depth, s.debug,
+                       ctx.slab[0], ctx.slab[1])
+
         def stage1():
-            return _C.rasterize_gaussians_backward_render(
-                s.bg, means3D, radii, colors_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp, s.viewmatrix, s.projmatrix,
-                s.tanfovx, s.tanfovy, s.kernel_size, g_color, g_coord, g_mcoord, g_depth, g_mdepth, g_alpha, g_normal, normal, sh,
-                s.sh_degree, s.campos, geom, ctx.num_rendered, binning, img, alpha, s.require_coord, s.require_depth, s.debug,
-                ctx.slab[0], ctx.slab[1])
+            return _C.rasterize_gaussians_backward_render(*stage1_args)
 
         def stage2(acc):
             return _C.rasterize_gaussians_backward_preprocess(
@@ -158,21 +205,38 @@ class _ShardedRasterize(torch.autograd.Function):
                 s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size, s.image_height, s.image_width, sh, s.sh_degree, s.campos, geom,
                 s.require_coord, s.require_depth, s.debug)
 
-        g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = backward_two_stage(stage1, stage2, ctx.group)
-        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, None, None, None
+        if ctx.exchange is not None:   # device-side exchange (or its dense fallback) owned by the caller
+            g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = stage2(ctx.exchange.backward_render(_C, *stage1_args))
+        else:
+            g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = backward_two_stage(stage1, stage2, ctx.group)
+        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, None, None, None, None
 
 
 class _GatherSlabs(torch.autograd.Function):
-    """all-reduce(sum) of slab-filled maps forward; identity backward (every rank holds the same full-image loss)."""
+    """All-gather of the ranks' slab rows into the whole map (pure copies: the gathered map holds exactly the bits each
+    rank rendered); identity backward (every rank holds the same full-image loss, and a rank's backward reads only the rows
+    of its own slab)."""
 
     @staticmethod
-    def forward(ctx, img, group):
-        out = img.detach().clone()
-        return allreduce_sum_(out, group)
+    def forward(ctx, img, group, pixel_rows, rank):
+        world = len(pixel_rows)
+        if not (dist.is_available() and dist.is_initialized()) or world == 1:
+            return img.detach().clone()
+        C, H, W = img.shape
+        hmax = max(e - b for b, e in pixel_rows)
+        b, e = pixel_rows[rank]
+        mine = img.new_zeros(C, hmax, W)
+        mine[:, : e - b] = img.detach()[:, b:e]
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        out = torch.empty_like(img)
+        for r, (rb, re) in enumerate(pixel_rows):
+            out[:, rb:re] = parts[r][:, : re - rb]
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        return grad_out, None
+        return grad_out, None, None, None
 
 
 class ShardedGaussianRasterizer(torch.nn.Module):
@@ -183,10 +247,12 @@ class ShardedGaussianRasterizer(torch.nn.Module):
     already-reduced parameter gradients.
     """
 
-    def __init__(self, raster_settings, rank: int | None = None, world_size: int | None = None, group=None, row_weights=None):
+    def __init__(self, raster_settings, rank: int | None = None, world_size: int | None = None, group=None, row_weights=None,
+                 exchange: GradExchange | None = None):
         super().__init__()
         self.raster_settings = raster_settings
         self.group = group
+        self.exchange = exchange   # a GradExchange created once by the caller (collective); None: one dense all-reduce per backward
         if world_size is None:
             world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         if rank is None:
@@ -204,17 +270,19 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         rotations = _absent() if rotations is None else rotations
         cov3D_precomp = _absent() if cov3D_precomp is None else cov3D_precomp
         return _ShardedRasterize.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                       self.raster_settings, self.slab, self.group)
+                                       self.raster_settings, self.slab, self.group, self.exchange)
 
     def pixel_rows(self) -> Tuple[int, int]:
         H = self.raster_settings.image_height
         return min(self.slab[0] * TILE, H), min(self.slab[1] * TILE, H)
 
     def gather_image(self, img: torch.Tensor) -> torch.Tensor:
-        """Sum of the slab images = the whole image (rows outside a rank's slab are zero).
+        """The whole [C,H,W] map from the ranks' slabs (all-gather of the slab rows; rows outside a rank's slab are zero locally).
 
         Differentiable: with the whole image on every rank an unchanged full-image loss (train.py:130-165: L1, SSIM,
         normal consistency) can be evaluated redundantly per rank; its gradient flows back unchanged and the sharded
         rasterizer's backward reads only the rows of its own slab, so nothing is counted twice.
         """
-        return _GatherSlabs.apply(img, self.group)
+        H = self.raster_settings.image_height
+        rows = [(min(b * TILE, H), min(e * TILE, H)) for b, e in self.slabs]
+        return _GatherSlabs.apply(img, self.group, rows, self.rank)

@@ -20,6 +20,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Plain `pytest tests` on a box without a CUDA device: GPU tests are skipped, not errors.  (On a GPU box nothing is
+    skipped here -- and the product itself still fails loudly without its extension, see tests/test_abi_host.py.)"""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run with -m gpu on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     lib.rgs_abi_version.restype = ctypes.c_int32
-    assert lib.rgs_abi_version() == 2
+    assert lib.rgs_abi_version() == 3
     lib.rgs_grad_stride.restype = ctypes.c_int32
     assert lib.rgs_grad_stride(0, 0) == 16 and lib.rgs_grad_stride(0, 1) == 16
     assert lib.rgs_grad_stride(1, 0) == 32 and lib.rgs_grad_stride(1, 1) == 32

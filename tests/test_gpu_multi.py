@@ -1,5 +1,7 @@
-"""Two-GPU test of the tile-row sharded rasterizer over NCCL (skipped on single-GPU boxes; the same control flow runs
-on CPU with gloo in tests/test_multigpu_host.py)."""
+"""Multi-GPU tests of the tile-row sharded rasterizer: world sizes 2, 4 and 8 (as many as the box has GPUs; skipped on
+single-GPU boxes).  One process per GPU; the images must be bit-identical to the single-GPU render, the gradients within the
+float tolerance, and -- with the device-side peer exchange -- bit-identical on every rank.  The same control flow runs on
+CPU with gloo in tests/test_multigpu_host.py."""
 import os
 import sys
 
@@ -12,69 +14,87 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, outdir, exchange):
-    os.environ["RGS_GRAD_EXCHANGE"] = exchange
+def _worker(rank, world, port, outdir, exchange_mode, variant):
     for p in (os.path.join(ROOT, "rade-gs_b200"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     import torch.distributed as dist
     import diff_gaussian_rasterization as dgr
     from rade_gs_b200 import scenes
-    from rade_gs_b200.multigpu import ShardedGaussianRasterizer
+    from rade_gs_b200.multigpu import GradExchange, ShardedGaussianRasterizer
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ex = None
     try:
+        coord, depth, ks = variant
         sc = scenes.make_scene(60000, 640, 400, 500.0, -3.8, seed=21, view=scenes.look_at_view((0.3, 0.2, -0.4), (0.0, 0.1, 6.0)), bg=(0.2, 0.1, 0.3)).to(dev)
-        st = dgr.GaussianRasterizationSettings(sc.height, sc.width, sc.tanfovx, sc.tanfovy, 0.1, sc.bg, 1.0, sc.viewmatrix, sc.projmatrix, 3, sc.campos,
-                                               False, True, True, False)
-        g = scenes.make_upstream_grads(sc.height, sc.width, seed=5, device=dev)
+        st = dgr.GaussianRasterizationSettings(sc.height, sc.width, sc.tanfovx, sc.tanfovy, ks, sc.bg, 1.0, sc.viewmatrix, sc.projmatrix, 3, sc.campos,
+                                               False, depth, coord, False)
+        P = sc.means3D.shape[0]
+        ex = GradExchange(P, dgr._C.grad_stride(coord, depth), dev, mode=exchange_mode)
+        assert ex.mode == exchange_mode
 
-        def run(rast):
-            lv = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+        def run(rast, seed, n=None):
+            g = scenes.make_upstream_grads(sc.height, sc.width, seed=seed, device=dev)
+            lv = {k: getattr(sc, k)[:n].clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
             m2 = torch.zeros_like(lv["means3D"], requires_grad=True)
-            color, radii, coord, mcoord, depth, mdepth, alpha, normal = rast(lv["means3D"], m2, lv["opacities"], shs=lv["shs"], scales=lv["scales"],
-                                                                             rotations=lv["rotations"])
-            loss = (color * g["color"]).sum() + (depth * g["depth"]).sum() + (normal * g["normal"]).sum() + (alpha * g["alpha"]).sum() + \
-                (coord * g["coord"]).sum() + (mdepth * g["mdepth"]).sum() + (mcoord * g["mcoord"]).sum()
+            color, radii, co, mco, dep, mdep, alpha, normal = rast(lv["means3D"], m2, lv["opacities"], shs=lv["shs"], scales=lv["scales"],
+                                                                    rotations=lv["rotations"])
+            loss = (color * g["color"]).sum() + (dep * g["depth"]).sum() + (normal * g["normal"]).sum() + (alpha * g["alpha"]).sum() + \
+                (co * g["coord"]).sum() + (mdep * g["mdepth"]).sum() + (mco * g["mcoord"]).sum()
             loss.backward()
-            return dict(color=color.detach(), depth=depth.detach(), normal=normal.detach(), coord=coord.detach(), radii=radii,
+            return dict(color=color.detach(), depth=dep.detach(), normal=normal.detach(), coord=co.detach(), alpha=alpha.detach(), radii=radii,
                         **{"g_" + k: v.grad for k, v in lv.items()}, g_means2D=m2.grad)
 
-        sharded = ShardedGaussianRasterizer(st)
-        a = run(sharded)
-        for k in ("color", "depth", "normal", "coord"):
-            a[k] = sharded.gather_image(a[k])          # sum of slabs = whole image
-        if rank == 0:
-            b = run(dgr.GaussianRasterizer(st))        # single-GPU answer on the same device
-            res = {}
+        sharded = ShardedGaussianRasterizer(st, exchange=ex)
+        single = dgr.GaussianRasterizer(st)
+        res = {}
+        # three steps on the same exchange object: different upstream gradients, then fewer Gaussians (rows re-associated), so the
+        # self-cleaning accumulators and the changed-rows bookkeeping of the exchange are exercised, not just its first call
+        for step, (seed, n) in enumerate(((5, None), (6, None), (7, P - 1234))):
+            a = run(sharded, seed, n)
+            for k in ("color", "depth", "normal", "coord", "alpha"):
+                a[k] = sharded.gather_image(a[k])
+            b = run(single, seed, n)                     # the single-GPU answer, computed on every rank's own GPU
             for k in a:
                 x, y = a[k].float(), b[k].float()
-                res[k] = (float((x - y).abs().max()), float(y.abs().max()), float((x - y).norm() / (y.norm() + 1e-30)))
-            np.save(os.path.join(outdir, "res.npy"), res, allow_pickle=True)
+                res[f"{step}/{k}"] = (float((x - y).abs().max()), float(y.abs().max()), float((x - y).norm() / (y.norm() + 1e-30)))
+            # are the replicated gradients the same bits on every rank?
+            flat = torch.cat([a[k].reshape(-1).float() for k in sorted(a) if k.startswith("g_")])
+            ref = flat.clone()
+            dist.broadcast(ref, src=0)
+            res[f"{step}/bits_differ_from_rank0"] = int((flat.view(torch.int32) != ref.view(torch.int32)).sum())
+        np.save(os.path.join(outdir, f"res{rank}.npy"), res, allow_pickle=True)
     finally:
+        if ex is not None:
+            ex.close()
         dist.destroy_process_group()
 
 
-_CASES = [(2, "dense"), (2, "sparse")]
-# Larger worlds only on request (RGS_TEST_WORLDS=4,8): in the one 8-GPU run this round the gathered colour map differed from
-# the single-GPU one by 1.5e-3 in a handful of pixels, although 8 slabs rendered on ONE GPU reproduce the whole image bit for
-# bit (tools/diag_slabs.py).  The cause (NCCL path at 8 ranks vs per-process state) is open; see DESIGN.md section 6.
-_CASES += [(int(w), "dense") for w in os.environ.get("RGS_TEST_WORLDS", "").split(",") if w.strip()]
+_WORLDS = [w for w in (2, 4, 8)]
+_VARIANTS = {"both_ks01": (True, True, 0.1), "depth_ks0": (False, True, 0.0), "coord_ks0": (True, False, 0.0)}
+_CASES = [(w, "peer", v) for w in _WORLDS for v in ("both_ks01",)] + [(2, "dense", "both_ks01"), (2, "peer", "depth_ks0"), (4, "peer", "coord_ks0"),
+                                                                      (8, "peer", "coord_ks0")]
 
 
-@pytest.mark.parametrize("world,exchange", _CASES)
-def test_sharded_equals_single(world, exchange, tmp_path):
-    """world ranks over NCCL against the single-GPU answer, with the dense all-reduce and the opt-in sparse row exchange."""
+@pytest.mark.parametrize("world,exchange,variant", _CASES)
+def test_sharded_equals_single(world, exchange, variant, tmp_path):
+    """`world` ranks against the single-GPU answer (computed on EVERY rank's GPU): images bit-exact, gradients within tolerance,
+    and identical bits on all ranks."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000 + world, str(tmp_path), exchange), nprocs=world, join=True)
-    res = np.load(tmp_path / "res.npy", allow_pickle=True).item()
-    for k in ("color", "depth", "normal", "coord"):
-        assert res[k][0] == 0.0, (k, res[k])          # slabs reproduce the single-GPU image bit for bit
-    assert res["radii"][0] == 0.0
-    for k, (mx, ref, rel) in res.items():
-        if k.startswith("g_"):
-            assert rel < 1e-3 and mx <= 1e-2 * ref + 1e-6, (k, mx, ref, rel)
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000 + world, str(tmp_path), exchange, _VARIANTS[variant]), nprocs=world, join=True)
+    for rank in range(world):
+        res = np.load(tmp_path / f"res{rank}.npy", allow_pickle=True).item()
+        for key, val in res.items():
+            step, k = key.split("/")
+            if k == "bits_differ_from_rank0":
+                assert val == 0, (rank, key, val)                 # replicated gradients: same bits everywhere
+            elif k in ("color", "depth", "normal", "coord", "alpha", "radii"):
+                assert val[0] == 0.0, (rank, key, val)            # slabs reproduce the single-GPU image bit for bit
+            else:
+                mx, ref, rel = val
+                assert rel < 1e-3 and mx <= 1e-2 * ref + 1e-6, (rank, key, val)

@@ -90,53 +90,3 @@ def test_model_saved_to_ply_renders_identically_after_loading(tmp_path):
     for a, b in zip(before, after):
         assert torch.equal(a, b)
     assert (before[1] > 0).sum() > 1000
-
-
-def test_fused_render_entry_point_matches_the_reference_style_call():
-    """`rade_gs_b200.renderer.render` (fused activations, split SH) against the call sequence of the reference's render()
-    (eager activations, concatenated SH): same maps bit for bit up to the activation's last-bit differences, same gradients."""
-    import diff_gaussian_rasterization as dgr
-    from rade_gs_b200 import renderer, scenes
-    from test_gpu_api import _settings
-    from test_gpu_fused import _ref_activate
-    from tolerances import grad_close_gpu
-
-    sc = scenes.make_scene(20_000, 256, 192, 220.0, -2.6, seed=13).to(DEV)
-    P = sc.means3D.shape[0]
-    filter_3D = torch.full((P, 1), 2e-3, device=DEV)
-
-    def make_pc():
-        m = _model(sc, filter_3D)
-        return SimpleNamespace(_xyz=m["xyz"], _scaling=m["scaling"], _opacity=m["opacity"], _rotation=m["rotation"], _features_dc=m["f_dc"],
-                               _features_rest=m["f_rest"], filter_3D=filter_3D, active_sh_degree=3)
-
-    cam = SimpleNamespace(image_height=sc.height, image_width=sc.width, FoVx=2 * math.atan(sc.tanfovx), FoVy=2 * math.atan(sc.tanfovy),
-                          world_view_transform=sc.viewmatrix, full_proj_transform=sc.projmatrix, camera_center=sc.campos)
-    pipe = SimpleNamespace(debug=False)
-    g = scenes.make_upstream_grads(sc.height, sc.width, seed=3, device=DEV)
-
-    def loss_of(pkg):
-        return (pkg["render"] * g["color"]).sum() + (pkg["expected_depth"] * g["depth"]).sum() + (pkg["normal"] * g["normal"]).sum() + \
-            (pkg["mask"] * g["alpha"]).sum()
-
-    pc = make_pc()
-    pkg = renderer.render(cam, pc, pipe, sc.bg, 0.1, require_coord=False, require_depth=True)
-    assert set(pkg) == {"render", "mask", "expected_coord", "median_coord", "expected_depth", "median_depth", "viewspace_points",
-                        "visibility_filter", "radii", "normal"}
-    loss_of(pkg).backward()
-
-    ref = make_pc()
-    s, o, r = _ref_activate(ref._scaling, ref._opacity, ref._rotation, filter_3D)
-    means2D = torch.zeros(P, 3, device=DEV, requires_grad=True)
-    out = dgr.GaussianRasterizer(_settings(dgr, sc, False, True, ks=0.1))(
-        means3D=ref._xyz, means2D=means2D, opacities=o, shs=torch.cat((ref._features_dc, ref._features_rest), dim=1), scales=s, rotations=r)
-    ref_pkg = {"render": out[0], "expected_depth": out[4], "normal": out[7], "mask": out[6]}
-    loss_of(ref_pkg).backward()
-
-    assert torch.equal(pkg["radii"], out[1])
-    for k in ("render", "expected_depth", "normal", "mask"):
-        d = (pkg[k] - ref_pkg[k]).abs()
-        assert (d > 1e-4 + 1e-4 * ref_pkg[k].abs()).float().mean().item() < 1e-4 and d.max().item() < 8e-3, (k, d.max().item())
-    for name in ("_xyz", "_scaling", "_opacity", "_rotation", "_features_dc", "_features_rest"):
-        grad_close_gpu(getattr(pc, name).grad.cpu().numpy(), getattr(ref, name).grad.cpu().numpy(), name, rel=2e-3, elem=1e-2)
-    grad_close_gpu(pkg["viewspace_points"].grad.cpu().numpy(), means2D.grad.cpu().numpy(), "viewspace_points", rel=2e-3, elem=1e-2)

@@ -97,20 +97,3 @@ def test_reader_rejects_garbage(tmp_path):
     p.write_bytes(b"ply\nformat binary_little_endian 1.0\nelement vertex 3\nproperty float x\nend_header\n\x00\x00")
     with pytest.raises(ValueError):
         ply_io.read_ply_vertices(str(p))
-
-
-def test_parameter_container_round_trips_through_ply(tmp_path):
-    import torch
-    from rade_gs_b200.model import GaussianParameters
-
-    m = {k: v.astype(np.float32) for k, v in _model(11, 2, seed=4).items()}
-    path = str(tmp_path / "pc.ply")
-    ply_io.save_gaussian_ply(path, **m)
-    pc = GaussianParameters.from_ply(path, device="cpu", max_sh_degree=2, requires_grad=True)
-    assert pc.num_points == 11 and pc.active_sh_degree == 2 and pc.max_sh_degree == 2
-    assert pc._features_rest.shape == (11, 8, 3) and pc._features_dc.shape == (11, 1, 3) and pc.filter_3D.shape == (11, 1)
-    assert pc._xyz.requires_grad and not pc.filter_3D.requires_grad and pc.get_xyz is pc._xyz
-    path2 = str(tmp_path / "again.ply")
-    pc.save_ply(path2)
-    assert open(path, "rb").read() == open(path2, "rb").read()  # byte-identical file
-    assert torch.equal(pc.to("cpu")._scaling, pc._scaling)

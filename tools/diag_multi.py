@@ -52,4 +52,9 @@ if world > 1:
         man = int((manual != whole[i]).sum())
         print(f"[rank {rank}] {n}: whole differs from rank 0's in {cross} elements; all_reduce(slabs) vs own whole: {coll}; all_gather+sum vs own whole: {man}",
               flush=True)
+        if (coll or man or cross) and rank == 0:
+            bad = torch.nonzero((summed != whole[i]) | (manual != whole[i]) | (mine != ref))[:6]
+            for c, y, x in bad.tolist():
+                print(f"    {n}[{c},{y},{x}] (tile row {y // 16}): whole {whole[i][c, y, x].item():.9g} all_reduce {summed[c, y, x].item():.9g} gather-sum {manual[c, y, x].item():.9g}"
+                      f" per-rank slab values {[round(t[c, y, x].item(), 9) for t in gathered]}", flush=True)
     dist.destroy_process_group()
