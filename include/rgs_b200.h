@@ -246,6 +246,14 @@ int32_t rgs_ssim_l1_forward(int32_t planes, int32_t H, int32_t W, const float* i
                             void* cuda_stream);
 int32_t rgs_ssim_l1_backward(int32_t planes, int32_t H, int32_t W, const float* img, const float* gt, const float* dmaps,
                              float w_ssim, float w_l1, const float* upstream, float* d_img, void* cuda_stream);
+/* Row-sharded form (multi-GPU, ABI 3): only SSIM-map / L1 rows [row_lo, row_hi) are counted; `img` must also hold the 5 halo rows
+ * either side of that range (the neighbouring ranks' pixels; zero padding applies at the true image border only).  Backward writes
+ * d_img for the block rows covering [row_lo - 5, row_hi + 5): the halo rows receive this rank's contribution to its neighbours'
+ * pixels; rows outside stay untouched (the caller zero-fills). */
+int32_t rgs_ssim_l1_forward_rows(int32_t planes, int32_t H, int32_t W, int32_t row_lo, int32_t row_hi, const float* img, const float* gt,
+                                 float* dmaps, double* sums, void* cuda_stream);
+int32_t rgs_ssim_l1_backward_rows(int32_t planes, int32_t H, int32_t W, int32_t row_lo, int32_t row_hi, const float* img, const float* gt,
+                                  const float* dmaps, float w_ssim, float w_l1, const float* upstream, float* d_img, void* cuda_stream);
 int32_t rgs_normal_consistency(int32_t H, int32_t W, int32_t from_depth, float inv_fx, float inv_fy, float cx, float cy,
                                const float* rendered_normal, const float* map_expected, const float* map_median,
                                float w_expected, float w_median, double* loss_sum, float* d_normal, float* d_expected,

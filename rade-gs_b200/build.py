@@ -60,7 +60,9 @@ def build_core(force=False, verbose=False) -> str:
         res = list(ex.map(one, CORE_SOURCES))
     objs = [o for o, _ in res]
     if force or any(ch for _, ch in res) or not os.path.exists(LIB):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared"], verbose)
+        tmp = LIB + ".tmp"   # link to a temporary name and rename: a snapshot of the tree never sees a half-written library
+        _run([NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared"], verbose)
+        os.replace(tmp, LIB)
         print("[build] wrote", LIB, flush=True)
     return LIB
 
@@ -78,9 +80,11 @@ def build_glue(force=False, verbose=False) -> str:
     _run(["g++", "-c", src, "-o", o, "-std=c++17", "-O2", "-fPIC", "-DTORCH_EXTENSION_NAME=_C", "-DTORCH_API_INCLUDE_EXTENSION_H", "-w"]
          + ["-I" + i for i in incs], verbose)
     libdir = os.path.dirname(LIB)
-    _run(["g++", "-shared", "-o", GLUE, o, "-L" + libdir, "-lrgs_b200"] + ["-L" + d for d in libdirs] +
+    tmp = GLUE + ".tmp"
+    _run(["g++", "-shared", "-o", tmp, o, "-L" + libdir, "-lrgs_b200"] + ["-L" + d for d in libdirs] +
          ["-L/usr/local/cuda/lib64", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart",
           "-Wl,-rpath,$ORIGIN/../rade_gs_b200"] + ["-Wl,-rpath," + d for d in libdirs], verbose)
+    os.replace(tmp, GLUE)
     print("[build] wrote", GLUE, flush=True)
     return GLUE
 

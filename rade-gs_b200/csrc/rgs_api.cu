@@ -238,7 +238,7 @@ static int64_t forward_to_binning(const rgs_camera* cam, const FwdParams& p, int
 		max_list = box[1];
 	}
 	static const bool force_radix = getenv("RGS_BINNING") != nullptr && std::string(getenv("RGS_BINNING")) == "radix";
-	const bool tile_path = !force_radix && max_list <= (uint32_t)TILE_SORT_CAP;
+	const bool tile_path = !force_radix;  // lists longer than the shared-memory sort take the multi-CTA path inside launch_tile_binning
 	const size_t sort_bytes = (R > 0 && !tile_path) ? sort_temp_bytes((size_t)R) : 0;
 	size_t bin_bytes = 0;
 	carve_bin(nullptr, (size_t)R, tiles, sort_bytes, &bin_bytes);
@@ -256,7 +256,7 @@ static int64_t forward_to_binning(const rgs_camera* cam, const FwdParams& p, int
 		StageScope sc(ST_BINNING, s);
 		launch_tile_binning(p, g, b, img, radii, R, max_list, s);
 	} else {
-		// a tile list too long for the shared-memory sort: global radix path (Gaussian-major offsets + 45-bit sort)
+		// cross-check only (RGS_BINNING=radix): the reference's own scheme, Gaussian-major offsets + one global 45-bit sort
 		StageScope sc(ST_BINNING, s);
 		launch_scan(g, P, s);
 		launch_binning(p, g, b, img, radii, R, s);
@@ -487,21 +487,33 @@ int32_t rgs_compute_3d_filter(int32_t P, const float* xyz, int32_t n_cams, const
 	return after_launch();
 }
 
-int32_t rgs_ssim_l1_forward(int32_t planes, int32_t H, int32_t W, const float* img, const float* gt, float* dmaps, double* sums, void* cuda_stream) {
+int32_t rgs_ssim_l1_forward_rows(int32_t planes, int32_t H, int32_t W, int32_t row_lo, int32_t row_hi, const float* img, const float* gt, float* dmaps,
+                                 double* sums, void* cuda_stream) {
 	if (planes < 0 || H <= 0 || W <= 0) return fail(RGS_E_INVALID, "image size must be positive");
+	if (row_lo < 0 || row_hi > H || row_lo > row_hi) return fail(RGS_E_INVALID, "row range out of the image");
 	if (!img || !gt || !sums) return fail(RGS_E_INVALID, "null pointer");
 	if (planes > 65535) return fail(RGS_E_INVALID, "too many image planes");
-	launch_ssim_l1_forward(planes, H, W, img, gt, dmaps, sums, (cudaStream_t)cuda_stream);
+	launch_ssim_l1_forward(planes, H, W, row_lo, row_hi, img, gt, dmaps, sums, (cudaStream_t)cuda_stream);
 	return after_launch();
+}
+
+int32_t rgs_ssim_l1_backward_rows(int32_t planes, int32_t H, int32_t W, int32_t row_lo, int32_t row_hi, const float* img, const float* gt,
+                                  const float* dmaps, float w_ssim, float w_l1, const float* upstream, float* d_img, void* cuda_stream) {
+	if (planes < 0 || H <= 0 || W <= 0) return fail(RGS_E_INVALID, "image size must be positive");
+	if (row_lo < 0 || row_hi > H || row_lo > row_hi) return fail(RGS_E_INVALID, "row range out of the image");
+	if (!img || !gt || !dmaps || !d_img) return fail(RGS_E_INVALID, "null pointer");
+	if (planes > 65535) return fail(RGS_E_INVALID, "too many image planes");
+	launch_ssim_l1_backward(planes, H, W, row_lo, row_hi, img, gt, dmaps, w_ssim, w_l1, upstream, d_img, (cudaStream_t)cuda_stream);
+	return after_launch();
+}
+
+int32_t rgs_ssim_l1_forward(int32_t planes, int32_t H, int32_t W, const float* img, const float* gt, float* dmaps, double* sums, void* cuda_stream) {
+	return rgs_ssim_l1_forward_rows(planes, H, W, 0, H, img, gt, dmaps, sums, cuda_stream);
 }
 
 int32_t rgs_ssim_l1_backward(int32_t planes, int32_t H, int32_t W, const float* img, const float* gt, const float* dmaps, float w_ssim, float w_l1,
                              const float* upstream, float* d_img, void* cuda_stream) {
-	if (planes < 0 || H <= 0 || W <= 0) return fail(RGS_E_INVALID, "image size must be positive");
-	if (!img || !gt || !dmaps || !d_img) return fail(RGS_E_INVALID, "null pointer");
-	if (planes > 65535) return fail(RGS_E_INVALID, "too many image planes");
-	launch_ssim_l1_backward(planes, H, W, img, gt, dmaps, w_ssim, w_l1, upstream, d_img, (cudaStream_t)cuda_stream);
-	return after_launch();
+	return rgs_ssim_l1_backward_rows(planes, H, W, 0, H, img, gt, dmaps, w_ssim, w_l1, upstream, d_img, cuda_stream);
 }
 
 int32_t rgs_normal_consistency(int32_t H, int32_t W, int32_t from_depth, float inv_fx, float inv_fy, float cx, float cy, const float* rendered_normal,

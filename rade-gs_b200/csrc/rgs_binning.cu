@@ -120,7 +120,8 @@ void launch_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, cons
 // Equal depth bits fall back to the Gaussian index through the low key half, which is exactly what the reference's
 // stable sort yields (instances are emitted in ascending Gaussian index).  Global traffic: 8 B + 8 B + 4 B (+ 8 B
 // for the exported keys) per instance instead of ~156 B.
-// Lists longer than TILE_SORT_CAP (shared-memory capacity) make the host take the radix path above instead.
+// Lists longer than TILE_SORT_CAP (shared-memory capacity) are split over several CTAs: chunk sort + global merge passes (below).
+// The global radix path above is kept only as a cross-check (`RGS_BINNING=radix`).
 // =====================================================================================================================
 
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int grid_x, int grid_y, int* __restrict__ tile_diff, uint32_t* __restrict__ tile_count,
@@ -320,20 +321,12 @@ __device__ __forceinline__ void cswap(uint64_t& a, uint64_t& b) {
 __device__ __forceinline__ int spad(int e) { return e + (e >> 4); }
 constexpr int SORT_THREADS = 128;
 
-__global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, int grid_x, int row_begin,
-                                                                  const uint64_t* __restrict__ local_keys, uint32_t* __restrict__ point_list,
-                                                                  uint64_t* __restrict__ keys_sorted, int cap) {
-	extern __shared__ uint64_t s_keys[];  // [2][spad(cap)]
-	const int tile = (blockIdx.y + row_begin) * grid_x + blockIdx.x;
-	const uint2 rg = ranges[tile];
-	const int n = (int)(rg.y - rg.x);
-	if (n == 0) return;
-	const int tid = threadIdx.x;
-	uint64_t* bufA = s_keys;
-	uint64_t* bufB = s_keys + spad(cap);
-	const uint64_t* src = local_keys + rg.x;
-	// runs of 8 straight from global memory: register sorting network (Batcher odd-even merge sort for 8 inputs)
-	for (int o0 = tid * SORT_VT; o0 < n; o0 += SORT_THREADS * SORT_VT) {
+// Sort `n` (<= the capacity the two buffers were sized for) 64-bit keys from global memory into shared memory; returns the
+// buffer that holds the sorted run.  Runs of 8 straight from global memory through a register network (Batcher odd-even merge
+// sort, 19 compare-exchanges), then merge-path passes ping-ponging between the two buffers.
+__device__ __forceinline__ uint64_t* sort_in_shared(const uint64_t* __restrict__ src, int n, uint64_t* bufA, uint64_t* bufB) {
+	const int tid = threadIdx.x, nthreads = blockDim.x;
+	for (int o0 = tid * SORT_VT; o0 < n; o0 += nthreads * SORT_VT) {
 		uint64_t k[SORT_VT];
 #pragma unroll
 		for (int q = 0; q < SORT_VT; q++) k[q] = (o0 + q < n) ? src[o0 + q] : KEY_MAX;
@@ -351,7 +344,7 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(const uint2* __
 	uint64_t* in = bufA;
 	uint64_t* out = bufB;
 	for (int L = SORT_VT; L < n; L <<= 1) {
-		for (int o0 = tid * SORT_VT; o0 < n; o0 += SORT_THREADS * SORT_VT) {
+		for (int o0 = tid * SORT_VT; o0 < n; o0 += nthreads * SORT_VT) {
 			const int base = (o0 / (2 * L)) * (2 * L);
 			const int a0 = base, lenA = min(L, n - base);
 			const int b0 = base + lenA, lenB = max(0, min(L, n - b0));
@@ -375,6 +368,19 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(const uint2* __
 		__syncthreads();
 		uint64_t* t = in; in = out; out = t;
 	}
+	return in;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, int grid_x, int row_begin,
+                                                                  const uint64_t* __restrict__ local_keys, uint32_t* __restrict__ point_list,
+                                                                  uint64_t* __restrict__ keys_sorted, int cap) {
+	extern __shared__ uint64_t s_keys[];  // [2][spad(cap)]
+	const int tile = (blockIdx.y + row_begin) * grid_x + blockIdx.x;
+	const uint2 rg = ranges[tile];
+	const int n = (int)(rg.y - rg.x);
+	if (n == 0 || n > cap) return;  // longer lists: the multi-CTA path below
+	const int tid = threadIdx.x;
+	const uint64_t* in = sort_in_shared(local_keys + rg.x, n, s_keys, s_keys + spad(cap));
 	uint32_t* dst = point_list + rg.x;
 	uint64_t* kdst = keys_sorted + rg.x;
 	const uint64_t tile_hi = (uint64_t)tile << 32;
@@ -385,17 +391,131 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(const uint2* __
 	}
 }
 
+// ---- tile lists longer than the shared-memory capacity: split -> sort chunks -> merge, several CTAs per tile ---------------------
+// Only the long tiles take this path; every other tile is finished by tile_sort_kernel above and is not touched here (the
+// CTAs of short tiles leave at once).  Grid = (tiles of the slab) x (chunks of the longest list).
+//   1. long_chunk_sort_kernel: CTA (tile, c) sorts elements [c*LONG_CHUNK, (c+1)*LONG_CHUNK) of the tile's segment in shared
+//      memory and writes the sorted run back in place;
+//   2. long_merge_kernel, run length L = LONG_CHUNK, 2*LONG_CHUNK, ...: CTA (tile, c) produces outputs [c*LONG_CHUNK, ...) of
+//      the merge of the pair of runs they fall into: two merge-path searches in global memory bound the input ranges, those
+//      LONG_CHUNK inputs are staged in shared memory, every thread merges LONG_VT consecutive outputs.  Ping-pong between the
+//      local-key buffer and the (not yet written) exported-key buffer of the same segment;
+//   3. long_finalize_kernel: local keys -> sorted ids + exported (tile | depth) keys.
+// Equal depth bits order by Gaussian index through the low key half, as everywhere else (the reference's stable radix sort).
+constexpr int LONG_CHUNK = 4096;
+constexpr int LONG_THREADS = 256;
+constexpr int LONG_VT = LONG_CHUNK / LONG_THREADS;
+
+__global__ void __launch_bounds__(LONG_THREADS) long_chunk_sort_kernel(const uint2* __restrict__ ranges, int grid_x, int row_begin, int cap,
+                                                                        uint64_t* __restrict__ local_keys) {
+	extern __shared__ uint64_t s_keys[];  // [2][spad(LONG_CHUNK)]
+	const int tile = (blockIdx.y + row_begin) * grid_x + blockIdx.x;
+	const uint2 rg = ranges[tile];
+	const int n = (int)(rg.y - rg.x);
+	const int c0 = blockIdx.z * LONG_CHUNK;
+	if (n <= cap || c0 >= n) return;
+	const int m = min(LONG_CHUNK, n - c0);
+	uint64_t* seg = local_keys + rg.x + c0;
+	const uint64_t* in = sort_in_shared(seg, m, s_keys, s_keys + spad(LONG_CHUNK));  // reads all of `seg` before its first barrier
+	for (int i = threadIdx.x; i < m; i += LONG_THREADS) seg[i] = in[spad(i)];
+}
+
+// smallest i in [max(0, d - lenB), min(d, lenA)] with A[i] > B[d - 1 - i]: the first d outputs of merge(A, B) take i from A
+__device__ __forceinline__ int merge_path(const uint64_t* __restrict__ A, int lenA, const uint64_t* __restrict__ B, int lenB, int d) {
+	int lo = max(0, d - lenB), hi = min(d, lenA);
+	while (lo < hi) {
+		const int mid = (lo + hi) >> 1;
+		if (A[mid] <= B[d - 1 - mid]) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+
+__global__ void __launch_bounds__(LONG_THREADS) long_merge_kernel(const uint2* __restrict__ ranges, int grid_x, int row_begin, int cap, int L,
+                                                                   const uint64_t* __restrict__ src, uint64_t* __restrict__ dst) {
+	__shared__ uint64_t s_in[LONG_CHUNK];
+	__shared__ int s_split[2];
+	const int tile = (blockIdx.y + row_begin) * grid_x + blockIdx.x;
+	const uint2 rg = ranges[tile];
+	const int n = (int)(rg.y - rg.x);
+	const int o0 = blockIdx.z * LONG_CHUNK;
+	if (n <= cap || o0 >= n) return;
+	const int o1 = min(n, o0 + LONG_CHUNK);
+	const int tid = threadIdx.x;
+	const int base = (o0 / (2 * L)) * (2 * L);
+	const int lenA = min(L, n - base), lenB = max(0, min(L, n - base - lenA));
+	const uint64_t* A = src + rg.x + base;
+	const uint64_t* B = A + lenA;
+	if (tid < 2) s_split[tid] = merge_path(A, lenA, B, lenB, (tid == 0 ? o0 : o1) - base);
+	__syncthreads();
+	const int a0 = s_split[0], a1 = s_split[1];
+	const int b0 = (o0 - base) - a0, b1 = (o1 - base) - a1;
+	const int na = a1 - a0, nb = b1 - b0;  // na + nb = o1 - o0 <= LONG_CHUNK
+	for (int i = tid; i < na; i += LONG_THREADS) s_in[i] = A[a0 + i];
+	for (int i = tid; i < nb; i += LONG_THREADS) s_in[na + i] = B[b0 + i];
+	__syncthreads();
+	const uint64_t* sA = s_in;
+	const uint64_t* sB = s_in + na;
+	const int total = na + nb;
+	const int d0 = min(total, tid * LONG_VT);
+	int i = merge_path(sA, na, sB, nb, d0), j = d0 - i;
+	uint64_t ka = i < na ? sA[i] : KEY_MAX, kb = j < nb ? sB[j] : KEY_MAX;
+	uint64_t* out = dst + rg.x + o0;
+#pragma unroll 4
+	for (int q = 0; q < LONG_VT; q++) {
+		if (d0 + q < total) {
+			const bool take_a = ka <= kb;
+			out[d0 + q] = take_a ? ka : kb;
+			if (take_a) { i++; ka = i < na ? sA[i] : KEY_MAX; } else { j++; kb = j < nb ? sB[j] : KEY_MAX; }
+		}
+	}
+}
+
+__global__ void __launch_bounds__(LONG_THREADS) long_finalize_kernel(const uint2* __restrict__ ranges, int grid_x, int row_begin, int cap,
+                                                                      const uint64_t* src, uint32_t* __restrict__ point_list, uint64_t* keys_sorted) {
+	const int tile = (blockIdx.y + row_begin) * grid_x + blockIdx.x;
+	const uint2 rg = ranges[tile];
+	const int n = (int)(rg.y - rg.x);
+	const int o0 = blockIdx.z * LONG_CHUNK;
+	if (n <= cap || o0 >= n) return;
+	const int o1 = min(n, o0 + LONG_CHUNK);
+	const uint64_t tile_hi = (uint64_t)tile << 32;
+	for (int i = o0 + threadIdx.x; i < o1; i += LONG_THREADS) {
+		const uint64_t k = src[rg.x + i];  // src may BE keys_sorted (odd number of merge passes): element-wise in place
+		point_list[rg.x + i] = (uint32_t)k;
+		keys_sorted[rg.x + i] = tile_hi | (k >> 32);
+	}
+}
+
 void launch_tile_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, const int* radii, int64_t R, uint32_t max_list, cudaStream_t s) {
 	if (R <= 0 || p.row_end <= p.row_begin) return;
 	scatter_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p.P, g.records, rec_floats(p.coord), g.depths, g.tiles_touched, radii, p.grid_x, p.grid_y,
 	                                                  p.row_begin, p.row_end, img.ranges, img.tile_count, b.keys_unsorted);
-	const int cap = (max((int)max_list, 256) + 255) & ~255;  // keys per ping-pong buffer
+	const int longest_short = (int)min(max_list, (uint32_t)TILE_SORT_CAP);
+	const int cap = (max(longest_short, 256) + 255) & ~255;  // keys per ping-pong buffer
 	const size_t smem = (size_t)2 * (cap + (cap >> 4)) * sizeof(uint64_t);
 	static size_t configured[64] = {};
 	if (smem > 48 * 1024) ensure_dynamic_smem(tile_sort_kernel, (size_t)2 * (TILE_SORT_CAP + (TILE_SORT_CAP >> 4)) * sizeof(uint64_t), configured);
 	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
 	tile_sort_kernel<<<grid, SORT_THREADS, smem, s>>>(img.ranges, p.grid_x, p.row_begin, b.keys_unsorted, b.point_list, b.keys_sorted, cap);
 	count_launch(2);
+	if (max_list > (uint32_t)TILE_SORT_CAP) {
+		const int chunks = (int)((max_list + LONG_CHUNK - 1) / LONG_CHUNK);
+		dim3 lgrid(p.grid_x, p.row_end - p.row_begin, chunks);
+		const size_t lsmem = (size_t)2 * (LONG_CHUNK + (LONG_CHUNK >> 4)) * sizeof(uint64_t);
+		static size_t lconfigured[64] = {};
+		ensure_dynamic_smem(long_chunk_sort_kernel, lsmem, lconfigured);
+		long_chunk_sort_kernel<<<lgrid, LONG_THREADS, lsmem, s>>>(img.ranges, p.grid_x, p.row_begin, TILE_SORT_CAP, b.keys_unsorted);
+		uint64_t* src = b.keys_unsorted;
+		uint64_t* dst = b.keys_sorted;
+		int launches = 2;
+		for (int64_t L = LONG_CHUNK; L < (int64_t)max_list; L <<= 1) {
+			long_merge_kernel<<<lgrid, LONG_THREADS, 0, s>>>(img.ranges, p.grid_x, p.row_begin, TILE_SORT_CAP, (int)L, src, dst);
+			uint64_t* t = src; src = dst; dst = t;
+			launches++;
+		}
+		long_finalize_kernel<<<lgrid, LONG_THREADS, 0, s>>>(img.ranges, p.grid_x, p.row_begin, TILE_SORT_CAP, src, b.point_list, b.keys_sorted);
+		count_launch(launches);
+	}
 }
 
 }  // namespace rgs

@@ -217,7 +217,7 @@ size_t sort_temp_bytes(size_t R);
 void launch_scan(GeomView g, int P, cudaStream_t s);
 void launch_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, const int* radii, int64_t R, cudaStream_t s);
 // tile-bucket binning (default path): per-tile counts -> ranges/totals -> scatter -> per-tile shared-memory sort
-constexpr int TILE_SORT_CAP = 8192;   // longest tile list the shared-memory sort takes (2 x 64 KB ping-pong); longer lists use the radix path
+constexpr int TILE_SORT_CAP = 8192;   // longest tile list the one-CTA shared-memory sort takes (2 x 64 KB ping-pong); longer lists: multi-CTA chunk sort + merge
 void launch_tile_scan(const FwdParams& p, ImgView img, cudaStream_t s);
 void launch_tile_binning(const FwdParams& p, GeomView g, BinView b, ImgView img, const int* radii, int64_t R, uint32_t max_list, cudaStream_t s);
 
@@ -273,9 +273,10 @@ size_t integrate_mask_words(int64_t R, int tiles);
 void launch_integrate(const FwdParams& p, GeomView g, BinView b, ImgView img, const int* radii, IntegrateView v, IntegrateOut out, cudaStream_t s);
 
 // fused image-side losses (rgs_image_loss.cu)
-void launch_ssim_l1_forward(int planes, int H, int W, const float* img, const float* gt, float* dmaps, double* sums, cudaStream_t s);
-void launch_ssim_l1_backward(int planes, int H, int W, const float* img, const float* gt, const float* dmaps, float w_ssim, float w_l1,
-                             const float* upstream, float* d_img, cudaStream_t s);
+void launch_ssim_l1_forward(int planes, int H, int W, int row_lo, int row_hi, const float* img, const float* gt, float* dmaps, double* sums,
+                            cudaStream_t s);
+void launch_ssim_l1_backward(int planes, int H, int W, int row_lo, int row_hi, const float* img, const float* gt, const float* dmaps, float w_ssim,
+                             float w_l1, const float* upstream, float* d_img, cudaStream_t s);
 void launch_normal_consistency(int H, int W, bool from_depth, float inv_fx, float inv_fy, float cx, float cy, const float* rendered_normal,
                                const float* map_e, const float* map_m, float w_e, float w_m, double* loss_sum, float* d_normal, float* d_e, float* d_m,
                                cudaStream_t s);

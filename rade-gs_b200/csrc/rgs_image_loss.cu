@@ -42,13 +42,17 @@ __device__ __forceinline__ void block_add(double* dst, float v, float* s_red) {
 	__syncthreads();
 }
 
-__global__ void __launch_bounds__(256) ssim_l1_forward_kernel(int H, int W, Window win, const float* __restrict__ img, const float* __restrict__ gt,
-                                                               float* __restrict__ dmaps, size_t map_stride, double* __restrict__ sums) {
+// Rows [row_lo, row_hi) are the rows whose SSIM-map / L1 values are counted (the whole image on one GPU; a rank's slab in the
+// row-sharded multi-GPU loss, where the neighbouring ranks' 5 halo rows around the slab are present in `img` but not counted);
+// block rows start at by0.
+__global__ void __launch_bounds__(256) ssim_l1_forward_kernel(int H, int W, int row_lo, int row_hi, int by0, Window win, const float* __restrict__ img,
+                                                               const float* __restrict__ gt, float* __restrict__ dmaps, size_t map_stride,
+                                                               double* __restrict__ sums) {
 	__shared__ float sA[IH][IW + 1], sB[IH][IW + 1];
 	__shared__ float sh[5][IH][TW];
 	__shared__ float s_red[8];
 	const int plane = blockIdx.z;
-	const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+	const int x0 = blockIdx.x * TW, y0 = (blockIdx.y + by0) * TH;
 	const float* A = img + (size_t)plane * H * W;
 	const float* B = gt + (size_t)plane * H * W;
 	for (int i = threadIdx.x; i < IH * IW; i += 256) {
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(256) ssim_l1_forward_kernel(int H, int W, Wind
 	for (int half = 0; half < 2; half++) {
 		const int ry = ty + 8 * half;
 		const int gy = y0 + ry, gx = x0 + tx;
-		if (gy < H && gx < W) {
+		if (gy >= row_lo && gy < row_hi && gx < W) {
 			float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
 			for (int k = 0; k < SW; k++) {
@@ -110,18 +114,20 @@ __global__ void __launch_bounds__(256) ssim_l1_forward_kernel(int H, int W, Wind
 	block_add(sums + 1, l1_sum, s_red);
 }
 
-__global__ void __launch_bounds__(256) ssim_l1_backward_kernel(int H, int W, Window win, const float* __restrict__ img, const float* __restrict__ gt,
-                                                                const float* __restrict__ dmaps, size_t map_stride, float w_ssim, float w_l1,
-                                                                const float* __restrict__ upstream, float* __restrict__ d_img) {
+// d_img is written for the rows of the launched blocks; only SSIM-map rows [row_lo, row_hi) contribute (dmaps outside are not read),
+// so rows further than 5 from that range come out as zero.
+__global__ void __launch_bounds__(256) ssim_l1_backward_kernel(int H, int W, int row_lo, int row_hi, int by0, Window win, const float* __restrict__ img,
+                                                                const float* __restrict__ gt, const float* __restrict__ dmaps, size_t map_stride,
+                                                                float w_ssim, float w_l1, const float* __restrict__ upstream, float* __restrict__ d_img) {
 	__shared__ float sM[3][IH][IW + 1];
 	__shared__ float sh[3][IH][TW];
 	const int plane = blockIdx.z;
-	const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+	const int x0 = blockIdx.x * TW, y0 = (blockIdx.y + by0) * TH;
 	const size_t base = (size_t)plane * H * W;
 	for (int i = threadIdx.x; i < IH * IW; i += 256) {
 		const int r = i / IW, c = i - r * IW;
 		const int gy = y0 + r - SR, gx = x0 + c - SR;
-		const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+		const bool in = gy >= row_lo && gy < row_hi && gx >= 0 && gx < W;
 		const size_t o = base + (size_t)gy * W + gx;
 		sM[0][r][c] = in ? __ldg(dmaps + o) : 0.f;
 		sM[1][r][c] = in ? __ldg(dmaps + o + map_stride) : 0.f;
@@ -155,7 +161,8 @@ __global__ void __launch_bounds__(256) ssim_l1_backward_kernel(int H, int W, Win
 			const size_t o = base + (size_t)gy * W + gx;
 			const float x = __ldg(img + o), y = __ldg(gt + o);
 			const float diff = x - y;
-			const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);  // torch.abs backward: sign(0) = 0
+			float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);  // torch.abs backward: sign(0) = 0
+			if (gy < row_lo || gy >= row_hi) sgn = 0.f;                  // L1 term of a row another rank counts
 			d_img[o] = up * (w_ssim * (t0 + 2.f * x * t1 + y * t2) + w_l1 * sgn);
 		}
 	}
@@ -291,17 +298,23 @@ Window make_window() {
 
 }  // namespace
 
-void launch_ssim_l1_forward(int planes, int H, int W, const float* img, const float* gt, float* dmaps, double* sums, cudaStream_t s) {
+void launch_ssim_l1_forward(int planes, int H, int W, int row_lo, int row_hi, const float* img, const float* gt, float* dmaps, double* sums,
+                            cudaStream_t s) {
 	cudaMemsetAsync(sums, 0, 2 * sizeof(double), s);
-	const dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, planes);
-	ssim_l1_forward_kernel<<<grid, 256, 0, s>>>(H, W, make_window(), img, gt, dmaps, (size_t)planes * H * W, sums);
+	if (row_hi <= row_lo) return;
+	const int by0 = row_lo / TH, by1 = (row_hi + TH - 1) / TH;
+	const dim3 grid((W + TW - 1) / TW, by1 - by0, planes);
+	ssim_l1_forward_kernel<<<grid, 256, 0, s>>>(H, W, row_lo, row_hi, by0, make_window(), img, gt, dmaps, (size_t)planes * H * W, sums);
 	count_launch();
 }
 
-void launch_ssim_l1_backward(int planes, int H, int W, const float* img, const float* gt, const float* dmaps, float w_ssim, float w_l1,
-                             const float* upstream, float* d_img, cudaStream_t s) {
-	const dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, planes);
-	ssim_l1_backward_kernel<<<grid, 256, 0, s>>>(H, W, make_window(), img, gt, dmaps, (size_t)planes * H * W, w_ssim, w_l1, upstream, d_img);
+void launch_ssim_l1_backward(int planes, int H, int W, int row_lo, int row_hi, const float* img, const float* gt, const float* dmaps, float w_ssim,
+                             float w_l1, const float* upstream, float* d_img, cudaStream_t s) {
+	if (row_hi <= row_lo) return;
+	const int by0 = max(0, row_lo - SR) / TH, by1 = (min(H, row_hi + SR) + TH - 1) / TH;
+	const dim3 grid((W + TW - 1) / TW, by1 - by0, planes);
+	ssim_l1_backward_kernel<<<grid, 256, 0, s>>>(H, W, row_lo, row_hi, by0, make_window(), img, gt, dmaps, (size_t)planes * H * W, w_ssim, w_l1, upstream,
+	                                             d_img);
 	count_launch();
 }
 

@@ -620,7 +620,8 @@ torch::Tensor image_input(const torch::Tensor& t, const torch::Tensor& like, con
 }
 
 // returns (sums [2] float64: sum of the SSIM map, sum |img - gt|; dmaps [3, planes, H, W] or empty)
-std::tuple<torch::Tensor, torch::Tensor> SsimL1Forward(const torch::Tensor& img, const torch::Tensor& gt, const bool need_grad) {
+std::tuple<torch::Tensor, torch::Tensor> SsimL1Forward(const torch::Tensor& img, const torch::Tensor& gt, const bool need_grad, const int row_lo_in,
+                                                        const int row_hi_in) {
 	TORCH_CHECK(img.dim() >= 2 && img.numel() == gt.numel() && img.size(-1) == gt.size(-1) && img.size(-2) == gt.size(-2),
 	            "ssim: images must have the same number of elements and the same [H, W]");
 	torch::Tensor a = image_input(img, img, "img1"), b = image_input(gt, img, "img2");
@@ -629,13 +630,14 @@ std::tuple<torch::Tensor, torch::Tensor> SsimL1Forward(const torch::Tensor& img,
 	const int planes = (int)(a.numel() / ((int64_t)H * W));
 	torch::Tensor sums = new_empty({2}, a.options().dtype(torch::kFloat64));
 	torch::Tensor dmaps = need_grad ? new_empty({3, planes, H, W}, a.options()) : torch::empty({0}, a.options());
-	check(rgs_ssim_l1_forward(planes, H, W, a.data_ptr<float>(), b.data_ptr<float>(), need_grad ? dmaps.data_ptr<float>() : nullptr,
-	                          sums.data_ptr<double>(), at::cuda::getCurrentCUDAStream().stream()));
+	const int row_lo = row_lo_in, row_hi = row_hi_in < 0 ? H : row_hi_in;  // (0, -1): the whole image
+	check(rgs_ssim_l1_forward_rows(planes, H, W, row_lo, row_hi, a.data_ptr<float>(), b.data_ptr<float>(), need_grad ? dmaps.data_ptr<float>() : nullptr,
+	                               sums.data_ptr<double>(), at::cuda::getCurrentCUDAStream().stream()));
 	return std::make_tuple(sums, dmaps);
 }
 
 torch::Tensor SsimL1Backward(const torch::Tensor& img, const torch::Tensor& gt, const torch::Tensor& dmaps, const double w_ssim, const double w_l1,
-                             const torch::Tensor& upstream) {
+                             const torch::Tensor& upstream, const int row_lo_in, const int row_hi_in) {
 	torch::Tensor a = image_input(img, img, "img1"), b = image_input(gt, img, "img2"), d = image_input(dmaps, img, "dmaps");
 	const c10::cuda::CUDAGuard guard(a.device());
 	const int H = a.size(-2), W = a.size(-1);
@@ -648,9 +650,11 @@ torch::Tensor SsimL1Backward(const torch::Tensor& img, const torch::Tensor& gt, 
 		up = image_input(upstream, img, "upstream gradient");
 		up_ptr = up.data_ptr<float>();
 	}
-	torch::Tensor out = new_empty(a.sizes(), a.options());
-	check(rgs_ssim_l1_backward(planes, H, W, a.data_ptr<float>(), b.data_ptr<float>(), d.data_ptr<float>(), (float)w_ssim, (float)w_l1, up_ptr,
-	                           out.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
+	const int row_lo = row_lo_in, row_hi = row_hi_in < 0 ? H : row_hi_in;
+	const bool whole = row_lo == 0 && row_hi == H;
+	torch::Tensor out = whole ? new_empty(a.sizes(), a.options()) : torch::zeros(a.sizes(), a.options());  // slab: rows far from the slab stay zero
+	check(rgs_ssim_l1_backward_rows(planes, H, W, row_lo, row_hi, a.data_ptr<float>(), b.data_ptr<float>(), d.data_ptr<float>(), (float)w_ssim,
+	                                (float)w_l1, up_ptr, out.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
 	return out.view(img.sizes());
 }
 
@@ -694,8 +698,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("rasterize_gaussians_split_sh", &RasterizeGaussiansSplitShCUDA);
 	m.def("rasterize_gaussians_backward_split_sh", &RasterizeGaussiansBackwardSplitShCUDA);
 	m.def("compute_3d_filter", &Compute3DFilter);
-	m.def("ssim_l1_forward", &SsimL1Forward);
-	m.def("ssim_l1_backward", &SsimL1Backward);
+	m.def("ssim_l1_forward", &SsimL1Forward, py::arg("img"), py::arg("gt"), py::arg("need_grad"), py::arg("row_lo") = 0, py::arg("row_hi") = -1);
+	m.def("ssim_l1_backward", &SsimL1Backward, py::arg("img"), py::arg("gt"), py::arg("dmaps"), py::arg("w_ssim"), py::arg("w_l1"), py::arg("upstream"),
+	      py::arg("row_lo") = 0, py::arg("row_hi") = -1);
 	m.def("normal_consistency", &NormalConsistency);
 	m.def("activate_forward", &ActivateForward);
 	m.def("activate_backward", &ActivateBackward);

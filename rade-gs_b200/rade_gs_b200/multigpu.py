@@ -286,3 +286,93 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         H = self.raster_settings.image_height
         rows = [(min(b * TILE, H), min(e * TILE, H)) for b, e in self.slabs]
         return _GatherSlabs.apply(img, self.group, rows, self.rank)
+
+
+# ---- slab-local image loss with halo rows (multi-GPU half) ----------------------------------------------------
+HALO = 5   # 11x11 SSIM window (utils/loss_utils.py:35: window_size=11, padding 5)
+
+
+def _exchange_rows(t: torch.Tensor, send_up, send_down, recv_up, recv_down, rank: int, world: int, group, add: bool):
+    """Neighbour exchange of row blocks of a [C,H,W] tensor: rows `send_up` go to rank-1, `send_down` to rank+1; what the
+    neighbours send lands in rows `recv_up` (from rank-1) / `recv_down` (from rank+1), overwriting or (add=True) accumulating."""
+    ops, bufs = [], []
+    for peer, srows, rrows in ((rank - 1, send_up, recv_up), (rank + 1, send_down, recv_down)):
+        if peer < 0 or peer >= world:
+            continue
+        if srows[1] > srows[0]:
+            ops.append(dist.P2POp(dist.isend, t[:, srows[0]:srows[1]].contiguous(), peer, group=group))
+        if rrows[1] > rrows[0]:
+            buf = torch.empty_like(t[:, rrows[0]:rrows[1]]).contiguous()
+            bufs.append((rrows, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, peer, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for (r0, r1), buf in bufs:
+        if add:
+            t[:, r0:r1] += buf
+        else:
+            t[:, r0:r1] = buf
+
+
+class _SlabSsimL1(torch.autograd.Function):
+    """(1 - l) * L1 + l * (1 - SSIM) of the WHOLE image (train.py:163), evaluated slab by slab: a rank counts the SSIM-map and L1
+    rows of its own slab; the 11x11 window reaches 5 rows into the neighbours' slabs, so 5 halo rows travel to each neighbour in
+    forward and the gradient a rank holds for its neighbours' halo pixels travels back (and is added) in backward.  Two scalars are
+    all-reduced; the image itself is never gathered.  `fwd` / `bwd` are the per-slab kernels (CUDA kernels in the product,
+    torch expressions in the CPU test): fwd(img, gt, r0, r1, need_grad) -> (sums[2] float64, state), bwd(img, gt, state, w_ssim,
+    w_l1, r0, r1) -> d_img [C,H,W] (non-zero in rows [r0-5, r1+5) only)."""
+
+    @staticmethod
+    def forward(ctx, image, gt, lambda_dssim, rows, rank, world, group, fwd, bwd):
+        r0, r1 = rows
+        H = image.shape[-2]
+        img = image.detach().clone()
+        # my first / last 5 rows are the neighbours' halos; theirs are mine
+        _exchange_rows(img, (r0, min(r0 + HALO, r1)), (max(r1 - HALO, r0), r1), (max(r0 - HALO, 0), r0), (r1, min(r1 + HALO, H)), rank, world, group, add=False)
+        sums, state = fwd(img, gt, r0, r1, ctx.needs_input_grad[0])
+        sums = sums.clone()
+        if world > 1:
+            dist.all_reduce(sums, group=group)
+        n = image.numel()
+        ctx.save_for_backward(img, gt, *state)
+        ctx.meta = (float(lambda_dssim), n, r0, r1, rank, world, group, bwd, H)
+        return ((1.0 - lambda_dssim) * sums[1] / n + lambda_dssim * (1.0 - sums[0] / n)).float()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        img, gt, *state = ctx.saved_tensors
+        lam, n, r0, r1, rank, world, group, bwd, H = ctx.meta
+        d = bwd(img, gt, state, -lam / n, (1.0 - lam) / n, r0, r1)
+        # rows [r0-5, r0) and [r1, r1+5) hold what MY slab's SSIM values contribute to the neighbours' pixels: send them home
+        _exchange_rows(d, (max(r0 - HALO, 0), r0), (r1, min(r1 + HALO, H)), (r0, min(r0 + HALO, r1)), (max(r1 - HALO, r0), r1), rank, world, group, add=True)
+        out = torch.zeros_like(d)
+        out[:, r0:r1] = d[:, r0:r1]
+        return out * grad_out, None, None, None, None, None, None, None, None
+
+
+def _cuda_slab_fwd(img, gt, r0, r1, need_grad):
+    from diff_gaussian_rasterization import _C
+    sums, dmaps = _C.ssim_l1_forward(img, gt, need_grad, r0, r1)
+    return sums, (dmaps,)
+
+
+def _cuda_slab_bwd(img, gt, state, w_ssim, w_l1, r0, r1):
+    from diff_gaussian_rasterization import _C
+    return _C.ssim_l1_backward(img, gt, state[0], w_ssim, w_l1, torch.empty(0), r0, r1)
+
+
+def slab_l1_ssim_loss(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float, pixel_rows: Tuple[int, int], rank: int | None = None,
+                      world_size: int | None = None, group=None, kernels=None) -> torch.Tensor:
+    """train.py:163's `(1 - l) * l1_loss(image, gt) + l * (1 - ssim(image, gt))` for a row-sharded render: `image` [3,H,W] holds this
+    rank's slab rows `pixel_rows` (`ShardedGaussianRasterizer.pixel_rows()`), `gt` the ground truth (at least those rows +- 5).
+    Returns the full-image loss (the same value on every rank); its gradient w.r.t. `image` is non-zero in this rank's rows only and
+    already contains the neighbours' contributions.  Slabs must be at least 5 rows tall (they are multiples of 16)."""
+    if world_size is None:
+        world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world_size > 1 and pixel_rows[1] - pixel_rows[0] < HALO:
+        raise ValueError("slab-local SSIM needs slabs of at least 5 pixel rows on every rank (a shorter slab breaks the neighbour halo exchange)")
+    fwd, bwd = kernels if kernels is not None else (_cuda_slab_fwd, _cuda_slab_bwd)
+    return _SlabSsimL1.apply(image, gt, float(lambda_dssim), (int(pixel_rows[0]), int(pixel_rows[1])), rank, world_size, group, fwd, bwd)

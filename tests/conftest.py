@@ -12,7 +12,7 @@ for p in (os.path.join(ROOT, "rade-gs_b200"), os.path.join(ROOT, "oracle"), ROOT
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 _ALL_GOLDEN = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz")) if os.path.isdir(GOLDEN_DIR) else []
-GOLDEN_CASES = [c for c in _ALL_GOLDEN if not c.startswith("integrate_")]       # rasterize fwd/bwd (tools/gen_golden.py)
+GOLDEN_CASES = [c for c in _ALL_GOLDEN if not c.startswith(("integrate_", "fused_"))]       # rasterize fwd/bwd (tools/gen_golden.py)
 INTEGRATE_CASES = [c for c in _ALL_GOLDEN if c.startswith("integrate_")]        # integrate (tools/gen_golden_integrate.py)
 
 

@@ -196,3 +196,29 @@ def test_training_step_slice_with_fused_losses():
     for k, t in leaves.items():
         assert t.grad is not None and torch.isfinite(t.grad).all(), k
     assert leaves["means3D"].grad.abs().max() > 0
+
+
+def test_row_range_ssim_kernels_add_up_to_the_whole_image():
+    """The row-sharded form of the L1 + SSIM kernels (multi-GPU slab-local loss): sums over disjoint row ranges add up to the
+    whole-image sums, and the per-range gradients (which reach 5 rows into the neighbouring ranges) add up to the whole gradient."""
+    import diff_gaussian_rasterization as dgr
+    C = dgr._C
+    g = torch.Generator().manual_seed(17)
+    H, W = 16 * 7 + 9, 150
+    gt = torch.rand(3, H, W, generator=g).to(DEV)
+    img = (gt + 0.2 * torch.randn(3, H, W, generator=g).to(DEV)).clamp(0, 1)
+    sums, dmaps = C.ssim_l1_forward(img, gt, True)
+    d_whole = C.ssim_l1_backward(img, gt, dmaps, -0.2, 0.8, torch.empty(0))
+    for cuts in ([0, 48, 80, H], [0, 16, 32, 64, 96, H]):
+        tot = torch.zeros(2, dtype=torch.float64, device=DEV)
+        d_sum = torch.zeros_like(img)
+        for r0, r1 in zip(cuts[:-1], cuts[1:]):
+            s, dm = C.ssim_l1_forward(img, gt, True, r0, r1)
+            tot += s
+            d = C.ssim_l1_backward(img, gt, dm, -0.2, 0.8, torch.empty(0), r0, r1)
+            far = d.clone()
+            far[:, max(r0 - 5, 0):min(r1 + 5, H)] = 0
+            assert not far.any()                              # nothing further than the 5 halo rows
+            d_sum += d
+        assert torch.allclose(tot, sums, rtol=1e-9, atol=1e-9)
+        assert torch.allclose(d_sum, d_whole, rtol=1e-5, atol=1e-7)

@@ -251,30 +251,84 @@ def _oracle_inputs(sc, coord, depth, ks, deg, shs=None):
                          rotations=sc.rotations.numpy(), sh_degree=deg, kernel_size=ks, require_coord=coord, require_depth=depth)
 
 
-def test_long_tile_list_takes_the_radix_path():
-    """A tile list longer than the shared-memory sort capacity (8192) must fall back to the global radix path and
-    still give the reference order: 12k splats piled onto a few pixels."""
+@pytest.mark.parametrize("n_splats", [12000, 20000, 70000])
+def test_long_tile_lists_take_the_multi_cta_sort(n_splats):
+    """Tile lists longer than the one-CTA shared-memory sort (8192) are split over several CTAs (chunk sort + global merge
+    passes; 2, 3 and 5 passes here, so both ping-pong parities) and must still give the reference order: splats piled onto a
+    few pixels.  No library sort is involved (the global radix path only runs when RGS_BINNING=radix asks for it)."""
     import oracle
     from rade_gs_b200 import rawapi, scenes
-    sc = scenes.make_scene(12000, 64, 48, 200.0, -4.0, seed=31)
-    sc.means3D[:, 0] = 0.02 * torch.randn(12000, generator=torch.Generator().manual_seed(1))
-    sc.means3D[:, 1] = 0.02 * torch.randn(12000, generator=torch.Generator().manual_seed(2))
-    sc.opacities[:] = 0.02  # keep transmittance alive so the whole list matters
+    sc = scenes.make_scene(n_splats, 64, 48, 200.0, -4.0, seed=31)
+    sc.means3D[:, 0] = 0.02 * torch.randn(n_splats, generator=torch.Generator().manual_seed(1))
+    sc.means3D[:, 1] = 0.02 * torch.randn(n_splats, generator=torch.Generator().manual_seed(2))
+    sc.opacities[:] = 0.02 * 12000 / n_splats  # keep transmittance alive so the whole list matters
     grads = scenes.make_upstream_grads(sc.height, sc.width, seed=32)
     fo = oracle.forward(_oracle_inputs(sc, False, True, 0.0, 3))
     scd = sc.to(DEV)
+    n0 = _C().launch_count()
     f = rawapi.forward(_C(), scd, False, True)
+    launches = _C().launch_count() - n0
     v = rawapi.ours_views(f, scd)
-    assert int(v["totals"][1]) > 8192, "scene did not produce a long tile list"
+    longest = int(v["totals"][1])
+    assert longest > 8192, "scene did not produce a long tile list"
+    passes = int(np.ceil(np.log2(np.ceil(longest / 4096))))
+    assert launches == 5 + 2 + passes, (launches, passes)   # preprocess, scan, scatter, tile sort, render + chunk sort, finalize + merge passes
     assert f["num_rendered"] == fo["num_rendered"]
     assert np.array_equal(v["point_list"].cpu().numpy().astype(np.uint32), fo["binning"]["point_list"])
     assert np.array_equal(v["ranges"].cpu().numpy().astype(np.uint32), fo["binning"]["ranges"])
+    keys = v["keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())
+    if n_splats > 12000:
+        return
     for k in ("color", "alpha", "depth", "normal"):
         image_close(f[k].cpu().numpy(), fo[k], IMG_OUTLIER_FRAC_CPU, k)
     b = rawapi.backward(_C(), scd, f, {k: v_.to(DEV) for k, v_ in grads.items()})
     bo = oracle.backward(_oracle_inputs(sc, False, True, 0.0, 3), fo, {k: v_.numpy() for k, v_ in grads.items()})
     for k in ("means3D", "sh", "opacity", "scales"):
         grad_close_cpu(b[k].cpu().numpy(), bo[k], k)
+
+
+def test_one_long_tile_inside_a_large_scene_leaves_the_other_tiles_alone():
+    """C1-sized scene (300k splats, 800x800) plus 12k small splats piled onto one spot: only the tiles under the pile take the
+    multi-CTA sort; every other tile's list, the images away from the pile and the reference build (when present) agree."""
+    from rade_gs_b200 import rawapi, scenes
+    sc, coord, depth = scenes.make_config("C1")
+    g = torch.Generator().manual_seed(9)
+    n_extra = 12000
+    pile = scenes.make_scene(n_extra, sc.width, sc.height, 1100.0, -6.0, seed=77)
+    pile.means3D[:, 0] = 0.5 + 0.004 * torch.randn(n_extra, generator=g)
+    pile.means3D[:, 1] = -0.3 + 0.004 * torch.randn(n_extra, generator=g)
+    pile.means3D[:, 2] = 4.0 + 0.5 * torch.rand(n_extra, generator=g)
+    pile.opacities[:] = 0.01
+    both = scenes.Scene(*[torch.cat([getattr(sc, k), getattr(pile, k)]) for k in ("means3D", "scales", "rotations", "opacities", "shs")],
+                        sc.viewmatrix, sc.projmatrix, sc.campos, sc.bg, sc.width, sc.height, sc.tanfovx, sc.tanfovy)
+    base, big = sc.to(DEV), both.to(DEV)
+    f0, f1 = rawapi.forward(_C(), base, coord, depth), rawapi.forward(_C(), big, coord, depth)
+    v0, v1 = rawapi.ours_views(f0, base), rawapi.ours_views(f1, big)
+    assert int(v0["totals"][1]) <= 8192 < int(v1["totals"][1])
+    r0, r1 = v0["ranges"].long(), v1["ranges"].long()
+    n0, n1 = r0[:, 1] - r0[:, 0], r1[:, 1] - r1[:, 0]
+    same = torch.nonzero(n0 == n1).squeeze(1)
+    assert same.numel() > 0.95 * n0.numel() and int((n1 > 8192).sum()) >= 1
+    # tiles the pile does not reach: identical sorted id lists (pile ids are >= P0, so equality of the lists says none leaked in)
+    pl0, pl1 = v0["point_list"].long(), v1["point_list"].long()
+    for t in same[torch.linspace(0, same.numel() - 1, 400).long()].tolist():
+        assert torch.equal(pl0[r0[t, 0]:r0[t, 1]], pl1[r1[t, 0]:r1[t, 1]]), t
+    keys = v1["keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())
+    tile_of = (keys >> 32).long()
+    assert bool((tile_of[r1[:, 0][n1 > 0]] == torch.nonzero(n1 > 0).squeeze(1)).all())
+    ref = None
+    try:
+        ref = _ref_module()
+    except pytest.skip.Exception:
+        pass
+    if ref is not None:
+        fr = rawapi.forward(ref, big, coord, depth)
+        vr = rawapi.ref_views(fr, big)
+        assert torch.equal(v1["point_list"], vr["point_list"]) and torch.equal(v1["keys"], vr["keys"]) and torch.equal(v1["ranges"], vr["ranges"])
+        for k in IMG_KEYS:
+            image_close(f1[k].cpu().numpy(), fr[k].cpu().numpy(), IMG_OUTLIER_FRAC_GPU, k)
 
 
 @pytest.mark.parametrize("M,deg,W,H", [(1, 0, 70, 50), (4, 1, 33, 17), (9, 2, 96, 64)])

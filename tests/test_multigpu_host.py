@@ -3,6 +3,7 @@ screen-space gradient rows -> replicated parameter gradients.  The CUDA stages a
 (oracle.render_backward / oracle.preprocess_backward), the control flow under test is
 rade_gs_b200.multigpu.backward_two_stage / allreduce_sum_ / partition_tile_rows -- the same code the GPU path runs
 with NCCL."""
+import math
 import os
 import sys
 
@@ -162,3 +163,73 @@ def test_sparse_row_exchange_equals_the_all_reduce(world, tmp_path):
             assert torch.allclose(r[case + "_sparse"].double(), total, rtol=1e-6, atol=1e-6)
             assert torch.allclose(r[case + "_dense"].double(), total, rtol=1e-6, atol=1e-6)
             assert torch.allclose(r[case + "_auto"].double(), total, rtol=1e-6, atol=1e-6)
+
+
+# ---- slab-local L1 + SSIM with halo rows: host logic on CPU (gloo), torch expressions standing in for the CUDA kernels -----------
+
+def _ssim_map(a, b):
+    """utils/loss_utils.py:35-63 restated (window 11, sigma 1.5, zero padding), returning the map."""
+    import torch.nn.functional as F
+    g = torch.tensor([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)], dtype=a.dtype)
+    g = g / g.sum()
+    w = (g[:, None] @ g[None, :])[None, None].expand(a.shape[0], 1, 11, 11).contiguous()
+    conv = lambda t: F.conv2d(t[None], w, padding=5, groups=a.shape[0])[0]  # noqa: E731
+    mu1, mu2 = conv(a), conv(b)
+    s1, s2, s12 = conv(a * a) - mu1 * mu1, conv(b * b) - mu2 * mu2, conv(a * b) - mu1 * mu2
+    return ((2 * mu1 * mu2 + 0.01 ** 2) * (2 * s12 + 0.03 ** 2)) / ((mu1 * mu1 + mu2 * mu2 + 0.01 ** 2) * (s1 + s2 + 0.03 ** 2))
+
+
+def _torch_slab_kernels():
+    def fwd(img, gt, r0, r1, need_grad):
+        return torch.stack([_ssim_map(img, gt)[:, r0:r1].sum().double(), (img - gt).abs()[:, r0:r1].sum().double()]), ()
+
+    def bwd(img, gt, state, w_ssim, w_l1, r0, r1):
+        with torch.enable_grad():   # called from inside an autograd backward, where grad mode is off
+            x = img.clone().requires_grad_(True)
+            (w_ssim * _ssim_map(x, gt)[:, r0:r1].sum() + w_l1 * (x - gt).abs()[:, r0:r1].sum()).backward()
+        return x.grad
+
+    return fwd, bwd
+
+
+def _slab_loss_worker(rank, world, port, tmpdir):
+    sys.path.insert(0, os.path.join(ROOT, "rade-gs_b200"))
+    from rade_gs_b200 import multigpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, W = 16 * 7, 40                     # 7 tile rows over 3 ranks: slabs of 3, 2, 2 tile rows
+        g = torch.Generator().manual_seed(5)
+        gt = torch.rand(3, H, W, generator=g, dtype=torch.float64)
+        whole = (gt + 0.2 * torch.randn(3, H, W, generator=g, dtype=torch.float64)).clamp(0, 1)
+        slabs = multigpu.partition_tile_rows(multigpu.tile_rows(H), world)
+        r0, r1 = slabs[rank][0] * 16, min(slabs[rank][1] * 16, H)
+        mine = torch.zeros_like(whole)
+        mine[:, r0:r1] = whole[:, r0:r1]
+        mine.requires_grad_(True)
+        loss = multigpu.slab_l1_ssim_loss(mine, gt, 0.2, (r0, r1), kernels=_torch_slab_kernels())
+        loss.backward()
+        torch.save({"loss": loss.detach(), "grad": mine.grad, "rows": (r0, r1), "whole": whole, "gt": gt}, os.path.join(tmpdir, f"slabloss{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_local_ssim_with_halo_rows_equals_the_whole_image_loss(tmp_path):
+    world = 3
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_slab_loss_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"slabloss{r}.pt") for r in range(world)]
+    x = res[0]["whole"].clone().requires_grad_(True)
+    gt = res[0]["gt"]
+    ref = 0.8 * (x - gt).abs().mean() + 0.2 * (1 - _ssim_map(x, gt).mean())      # train.py:163 on the whole image, one process
+    ref.backward()
+    grad = torch.zeros_like(x)
+    for r in res:
+        assert abs(float(r["loss"]) - float(ref)) < 1e-6, (float(r["loss"]), float(ref))   # the loss is returned as float32
+        r0, r1 = r["rows"]
+        out = r["grad"].clone()
+        out[:, r0:r1] = 0
+        assert not out.any()                                 # a rank's gradient lives in its own rows only
+        grad[:, r0:r1] = r["grad"][:, r0:r1]
+    assert torch.allclose(grad, x.grad, rtol=1e-9, atol=1e-12)  # including the rows next to slab boundaries (halo contributions)
