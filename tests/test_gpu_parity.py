@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN_CASES, ROOT, golden_oracle_inputs, golden_upstream, load_golden
-from tolerances import IMG_OUTLIER_FRAC_CPU, IMG_OUTLIER_FRAC_GPU, grad_close_cpu, grad_close_gpu, image_close
+from tolerances import grad_close_vs_reference_runs, IMG_OUTLIER_FRAC_CPU, IMG_OUTLIER_FRAC_GPU, grad_close_cpu, grad_close_gpu, image_close
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -111,9 +111,16 @@ def _ref_module():
     return build_ref.load()
 
 
-@pytest.mark.parametrize("cfg,ks", [("C1", 0.0), ("C1", 0.1)])
-def test_against_reference_build_c1(cfg, ks):
-    """BASELINE config[1] (300k splats, 800x800, depth variant) next to the reference's own CUDA build."""
+_SPREAD_LOG = os.path.join(ROOT, "gpurun_out", "parity_refbuild.jsonl")
+
+
+@pytest.mark.parametrize("cfg,ks", [("C1", 0.0), ("C1", 0.1), ("C2", 0.0), ("C3", 0.0), ("C4", 0.0)])
+def test_against_reference_build(cfg, ks):
+    """BASELINE configs C1 (300k, 800x800), C2 (1M, 1600x1200, headline), C3 (3M, 1920x1080, coordinate map) and C4 (10M,
+    4096x4096) next to the reference's own CUDA build on identical inputs: every integer quantity bit-exact, images within the
+    stated tolerance, every gradient tensor within 1e-3 relative L2 on the rows the reference itself determines (its atomics make two
+    of ITS runs differ; see tolerances.grad_close_vs_reference_runs; the statistics are logged to gpurun_out/parity_refbuild.jsonl)."""
+    import json
     from rade_gs_b200 import rawapi, scenes
     ref = _ref_module()
     sc, coord, depth = scenes.make_config(cfg)
@@ -125,17 +132,30 @@ def test_against_reference_build_c1(cfg, ks):
     assert torch.equal(fo["radii"], fr["radii"])
     assert torch.equal(vo["point_list"], vr["point_list"]) and torch.equal(vo["keys"], vr["keys"]) and torch.equal(vo["ranges"], vr["ranges"])
     assert (vo["n_contrib"] != vr["n_contrib"]).float().mean().item() < 1e-5
+    rec = {"cfg": cfg, "ks": ks, "num_rendered": int(fo["num_rendered"]), "n_contrib_mismatch": int((vo["n_contrib"] != vr["n_contrib"]).sum()),
+           "images_max_abs": {}, "grads": {}}
     for k in IMG_KEYS:
         image_close(fo[k].cpu().numpy(), fr[k].cpu().numpy(), IMG_OUTLIER_FRAC_GPU, k)
+        rec["images_max_abs"][k] = float((fo[k] - fr[k]).abs().max())
+    del vo, vr
     bo = rawapi.backward(_C(), sc, fo, grads)
+    bo2 = rawapi.backward(_C(), sc, fo, grads)
     br1, br2 = rawapi.backward(ref, sc, fr, grads), rawapi.backward(ref, sc, fr, grads)
+    failures = []
     for k in GRAD_KEYS:
-        refm = 0.5 * (br1[k].double() + br2[k].double())
-        # the reference's own run-to-run spread (atomic order; rotations / scales carry cancellation) sets the scale: both
-        # its max-norm and its L2 form, with head-room for one more independent draw (ours)
-        noise = ((br1[k] - br2[k]).abs().max() / (refm.abs().max() + 1e-30)).item()
-        noise = max(noise, ((br1[k] - br2[k]).double().norm() / (refm.norm() + 1e-30)).item())
-        grad_close_gpu(bo[k].cpu().numpy(), refm.cpu().numpy(), k, rel=1e-3 + 4 * noise, elem=1e-3 + 4 * noise)
+        try:
+            rec["grads"][k] = grad_close_vs_reference_runs(bo[k].cpu().numpy(), br1[k].cpu().numpy(), br2[k].cpu().numpy(), k)
+            nrm = 0.5 * (br1[k].double() + br2[k].double()).norm().item() + 1e-30
+            rec["grads"][k]["ours_vs_ours_relL2_all_rows"] = (bo[k] - bo2[k]).double().norm().item() / nrm
+        except AssertionError as e:
+            failures.append(str(e))
+    try:
+        os.makedirs(os.path.dirname(_SPREAD_LOG), exist_ok=True)
+        with open(_SPREAD_LOG, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except OSError:
+        pass
+    assert not failures, failures
 
 
 # ---- size-independent properties at the headline size (1M splats, 1600x1200) -----------------------------------------

@@ -51,7 +51,7 @@ torch.set_num_threads(4)
 
 
 def n(t):
-    return t.detach().cpu().numpy()
+    return t.detach().cpu().numpy().copy()          # a copy: several tensors are updated in place afterwards
 
 
 def gen_losses():
