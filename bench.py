@@ -284,17 +284,19 @@ def main():
     slab = multigpu.partition_tile_rows(grid_y, world)[rank] if multi else (0, grid_y)
     E = torch.Tensor([])
     exchange = multigpu.GradExchange(P, C.grad_stride(coord, depth), dev) if multi else None
+    # multi-GPU: the maps are compact ([C, slab rows, W]); the upstream gradients of a rank are the rows of its slab
+    sgrads = {k: v[:, min(slab[0] * 16, H):min(slab[1] * 16, H)].contiguous() for k, v in grads.items()} if multi else grads
 
     def step_resident():
         if not multi:
             f = rawapi.forward(C, sc, coord, depth)
             return f, rawapi.backward(C, sc, f, grads)
         out = C.rasterize_gaussians_slab(sc.bg, sc.means3D, E, sc.opacities, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix, sc.projmatrix,
-                                         sc.tanfovx, sc.tanfovy, 0.0, H, W, sc.shs, 3, sc.campos, False, coord, depth, False, slab[0], slab[1])
+                                         sc.tanfovx, sc.tanfovy, 0.0, H, W, sc.shs, 3, sc.campos, False, coord, depth, False, slab[0], slab[1], True)
         acc = exchange.backward_render(C, sc.bg, sc.means3D, out[8], E, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix, sc.projmatrix,
-                                       sc.tanfovx, sc.tanfovy, 0.0, grads["color"], grads["coord"], grads["mcoord"], grads["depth"],
-                                       grads["mdepth"], grads["alpha"], grads["normal"], out[5], sc.shs, 3, sc.campos, out[9], out[0],
-                                       out[10], out[11], out[4], coord, depth, False, slab[0], slab[1])
+                                       sc.tanfovx, sc.tanfovy, 0.0, sgrads["color"], sgrads["coord"], sgrads["mcoord"], sgrads["depth"],
+                                       sgrads["mdepth"], sgrads["alpha"], sgrads["normal"], out[5], sc.shs, 3, sc.campos, out[9], out[0],
+                                       out[10], out[11], out[4], coord, depth, False, slab[0], slab[1], True, H)
         g = C.rasterize_gaussians_backward_preprocess(acc, sc.bg, sc.means3D, out[8], E, sc.opacities, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix,
                                                       sc.projmatrix, sc.tanfovx, sc.tanfovy, 0.0, H, W, sc.shs, 3, sc.campos, out[9], coord, depth, False)
         return {"num_rendered": out[0]}, g
@@ -365,7 +367,7 @@ def main():
             if ours:
                 st = dgr.GaussianRasterizationSettings(H, W, sc.tanfovx, sc.tanfovy, 0.0, dbuf["bg"], 1.0, dbuf["view"], dbuf["proj"], 3, dbuf["campos"],
                                                        False, depth, coord, False)
-                rast = multigpu.ShardedGaussianRasterizer(st, rank=rank, world_size=world, exchange=exchange) if multi else dgr.GaussianRasterizer(st)
+                rast = multigpu.ShardedGaussianRasterizer(st, rank=rank, world_size=world, exchange=exchange, compact=True) if multi else dgr.GaussianRasterizer(st)
                 color, radii, co, mco, dep, mdep, alpha, normal = rast(leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"],
                                                                         scales=leaves["scales"], rotations=leaves["rotations"])
             else:
@@ -374,10 +376,11 @@ def main():
                 color, radii, co, mco, dep, mdep, alpha, normal = _RefFunction.apply(C, scd, coord, depth, 0.0, leaves["means3D"], means2D, leaves["shs"],
                                                                                      leaves["opacities"], leaves["scales"], leaves["rotations"])
             torch.cuda.current_stream().wait_stream(copy_stream)
-            sl = slice(r0, r1)
+            sl = slice(0, r1 - r0) if multi else slice(r0, r1)   # compact maps start at the slab's first row
+            gsl = slice(r0, r1)
             # photometric L1 against the 8-bit ground truth + small regularisers that keep the depth / normal / alpha gradient
             # paths live (stand-ins for train.py's depth-normal consistency terms, which also need no ground truth)
-            loss = (color[:, sl] - dbuf["gt_color"][:, sl].float() * (1.0 / 255.0)).abs().mean() + 0.01 * alpha[:, sl].mean()
+            loss = (color[:, sl] - dbuf["gt_color"][:, gsl].float() * (1.0 / 255.0)).abs().mean() + 0.01 * alpha[:, sl].mean()
             if depth:
                 loss = loss + 0.05 * dep[:, sl].mean()
             if coord:
@@ -456,7 +459,8 @@ def main():
             "impl": a.impl,
             "config": {"workload": f"{a.config}: {P} random-init Gaussians (SURVEY app. C seed 1234), {W}x{H}, SH deg 3, "
                                    f"require_depth={depth} require_coord={coord}, fwd+bwd at the _C boundary, num_rendered={R if not multi else 'per-slab'}",
-                       "parallelism": (f"tile-row slabs x{world}, gradient-row exchange: {exchange.mode}" if multi else "single GPU"),
+                       "parallelism": (f"tile-row slabs x{world}, gradient-row exchange: {exchange.mode}" + (f" (peer self-check failed: {exchange.fallback_reason})" if exchange.fallback_reason else "")
+                                       if multi else "single GPU"),
                        "l2": "per-step working set (192 MB SH + 248 MB SH grads + 64 MB records + sort buffers) exceeds the 126 MB L2; no explicit flush",
                        "protocol": f"median of {t_res['iterations']} per-iteration CUDA-event times ({t_res['windows']} windows of {a.steps} steps, barrier+synchronize around each window, max over ranks per iteration)"},
             "timing": t_res,

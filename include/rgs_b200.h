@@ -63,6 +63,11 @@ typedef struct rgs_camera {
 	/* Tile-row slab rendered by this call: tile rows [tile_row_begin, tile_row_end).  (0, -1) = whole
 	 * image.  Multi-GPU row sharding (DESIGN.md "Multi-GPU"); the reference has no equivalent.       */
 	int32_t tile_row_begin, tile_row_end;
+	/* ABI 3: compact_slab != 0 -> every [C,H,W] map of this call (forward outputs; backward's upstream gradients, alpha and
+	 * normal maps) holds ONLY the pixel rows of the slab, i.e. is [C, Hs, W] with Hs = min(tile_row_end*16, H) - tile_row_begin*16.
+	 * Per-rank image memory, its zero-fill and the image-side scratch then scale with 1/ranks.  0 = full-size maps whose rows
+	 * outside the slab the library does not touch. */
+	int32_t compact_slab;
 } rgs_camera;
 
 /* Per-Gaussian model inputs (rasterize_points.h:18-41). */
@@ -204,6 +209,9 @@ const float* rgs_exchange_result(rgs_exchange* ex);    /* summed rows, valid aft
 int32_t rgs_exchange_rows(rgs_exchange* ex, int32_t P, const uint32_t* tiles_touched, const int32_t* radii, void* cuda_stream);
 int32_t rgs_backward_render_exchange(const rgs_camera* cam, const rgs_gaussians* g, const rgs_backward_in* in, rgs_exchange* ex,
                                      void* cuda_stream);
+/* Synchronises the stream and returns 0 when every barrier so far completed, 1 + p when one gave up (after ~10 s) waiting for
+ * rank p -- the rows of that step are then meaningless; callers fall back to a host-driven collective. */
+int32_t rgs_exchange_status(rgs_exchange* ex, void* cuda_stream);
 const char* rgs_exchange_last_error(void);
 
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:18-23, rasterizer_impl.cu:176-188). */

@@ -142,6 +142,13 @@ static int make_params(const rgs_camera* cam, const rgs_gaussians* g, FwdParams&
 	p.row_begin = cam->tile_row_begin;
 	p.row_end = cam->tile_row_end < 0 ? p.grid_y : cam->tile_row_end;
 	if (p.row_begin < 0 || p.row_end > p.grid_y || p.row_begin > p.row_end) return fail(RGS_E_INVALID, "tile row slab out of range");
+	p.py_off = 0;
+	p.Hs = cam->height;
+	if (cam->compact_slab) {
+		p.py_off = p.row_begin * TILE_Y;
+		p.Hs = (p.row_end * TILE_Y < cam->height ? p.row_end * TILE_Y : cam->height) - p.py_off;
+		if (p.Hs < 0) p.Hs = 0;
+	}
 	p.tan_fovx = cam->tan_fovx;
 	p.tan_fovy = cam->tan_fovy;
 	// focal lengths computed on the host in float, as the reference does (rasterizer_impl.cu:288-289)
@@ -204,7 +211,7 @@ static int64_t forward_to_binning(const rgs_camera* cam, const FwdParams& p, int
                                   BinView& b, ImgView& img) {
 	int rc;
 	const int P = p.P;
-	const size_t N = (size_t)p.W * p.H;
+	const size_t N = (size_t)p.W * p.Hs;
 	const int tiles = p.grid_x * p.grid_y;
 
 	// image-side scratch first: needed even when there is nothing to draw (background fill)
@@ -291,6 +298,7 @@ int64_t rgs_integrate(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_
 	c.require_coord = 0;
 	c.tile_row_begin = 0;
 	c.tile_row_end = -1;
+	c.compact_slab = 0;
 	FwdParams p;
 	int rc = make_params(&c, gs, p);
 	if (rc != RGS_OK) return rc;
@@ -349,7 +357,7 @@ static int backward_views(const rgs_camera* cam, const rgs_gaussians* gs, const 
 	int rc = make_params(cam, gs, p);
 	if (rc != RGS_OK) return rc;
 	if (!in || !in->geom_buffer || !in->image_buffer) return fail(RGS_E_INVALID, "null backward inputs / buffers");
-	const size_t N = (size_t)p.W * p.H;
+	const size_t N = (size_t)p.W * p.Hs;
 	const size_t scan_bytes = p.P > 0 ? scan_temp_bytes(p.P) : 0;
 	g = carve_geom(const_cast<char*>(in->geom_buffer), p.P, p.coord, scan_bytes, nullptr);
 	const size_t sort_bytes = in->num_rendered > 0 ? sort_temp_bytes((size_t)in->num_rendered) : 0;
@@ -531,7 +539,12 @@ int32_t rgs_debug_get_views(const rgs_camera* cam, int32_t P, int64_t num_render
 	if (!cam || !views) return fail(RGS_E_INVALID, "null pointer");
 	const bool coord = cam->require_coord != 0, depth = cam->require_depth != 0;
 	const int grid_x = (cam->width + TILE_X - 1) / TILE_X, grid_y = (cam->height + TILE_Y - 1) / TILE_Y;
-	const size_t N = (size_t)cam->width * cam->height;
+	size_t N = (size_t)cam->width * cam->height;
+	if (cam->compact_slab) {
+		const int r1 = cam->tile_row_end < 0 ? grid_y : cam->tile_row_end;
+		const int hs = (r1 * TILE_Y < cam->height ? r1 * TILE_Y : cam->height) - cam->tile_row_begin * TILE_Y;
+		N = (size_t)cam->width * (hs > 0 ? hs : 0);
+	}
 	const size_t scan_bytes = P > 0 ? scan_temp_bytes(P) : 0;
 	GeomView g = carve_geom(const_cast<char*>(geom_buffer), P, coord, scan_bytes, nullptr);
 	const size_t sort_bytes = num_rendered > 0 ? sort_temp_bytes((size_t)num_rendered) : 0;

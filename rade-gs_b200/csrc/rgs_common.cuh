@@ -202,6 +202,7 @@ struct FwdParams {
 	int P, D, M, W, H;
 	int grid_x, grid_y;       // tiles in the full image
 	int row_begin, row_end;   // slab of tile rows handled by this call
+	int py_off, Hs;           // pixel row stored first in the [C,Hs,W] maps of this call and their height (0, H unless compact_slab)
 	float tan_fovx, tan_fovy, focal_x, focal_y, kernel_size, scale_modifier;
 	bool coord, depth;        // variant (normal := coord || depth, forward.cu:732-739)
 	const float *means3D, *opacities, *shs, *shs_rest, *colors_precomp, *scales, *rotations, *cov3D_precomp;

@@ -21,30 +21,39 @@ __global__ void __launch_bounds__(128, 4) preprocess_backward_kernel(FwdParams p
                                                                    const float* __restrict__ grad_accum, ParamGradOut out, int fix_mip) {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= p.P) return;
-	const bool visible = radii[idx] > 0;
+	bool visible = radii[idx] > 0;
 
 	float o_means2D[3] = {0, 0, 0}, o_colors[3] = {0, 0, 0}, o_opacity = 0.f, o_mean3D[3] = {0, 0, 0};
 	float o_cov[6] = {0, 0, 0, 0, 0, 0}, o_scale[3] = {0, 0, 0}, o_rot[4] = {0, 0, 0, 0};
 
+	float gr[GRAD_FLOATS_COORD];
 	if (visible) {
 		const int GF = grad_floats(p.coord);
 		const float* ga = grad_accum + (size_t)idx * GF;
-		float gr[GRAD_FLOATS_COORD];
+		bool any = false;
 #pragma unroll
 		for (int i = 0; i < GRAD_FLOATS_BASE / 4; i++) {
 			const float4 v = *reinterpret_cast<const float4*>(ga + 4 * i);
 			gr[4 * i] = v.x; gr[4 * i + 1] = v.y; gr[4 * i + 2] = v.z; gr[4 * i + 3] = v.w;
+			any = any || v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
 		}
 		if (p.coord) {
 #pragma unroll
 			for (int i = GRAD_FLOATS_BASE / 4; i < GRAD_FLOATS_COORD / 4; i++) {
 				const float4 v = *reinterpret_cast<const float4*>(ga + 4 * i);
 				gr[4 * i] = v.x; gr[4 * i + 1] = v.y; gr[4 * i + 2] = v.z; gr[4 * i + 3] = v.w;
+				any = any || v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
 			}
 		} else {
 #pragma unroll
 			for (int i = GRAD_FLOATS_BASE; i < GRAD_FLOATS_COORD; i++) gr[i] = 0.f;
 		}
+		// A rendered splat no pixel received (occluded, or below 1/255 everywhere) has an all-zero row: every output of the chain
+		// below is a sum of products with those zeros (the reference computes exactly 0 for it), so skip the chain and its loads.
+		// NaN rows compare unequal to zero and take the full path.
+		visible = any;
+	}
+	if (visible) {
 
 		const float* V = p.viewmatrix;
 		const float h_x = p.focal_x, h_y = p.focal_y;
@@ -364,14 +373,18 @@ __global__ void __launch_bounds__(128, 4) preprocess_backward_kernel(FwdParams p
 constexpr int SH_WARPS = 8;
 
 // `count` rows of `width` floats, contiguous in global memory, <-> columns [col0, col0 + width) of the padded shared tile
+// `rows` (loads only): bit r set = row r is wanted; the 16-byte chunks of the other rows are not fetched (their slots are
+// overwritten with zeros by the owner lane afterwards).
 template <bool TO_SHARED>
-__device__ __forceinline__ void sh_block_copy(float* tile, int stride, int col0, int width, int count, const float* src, float* dst, int lane) {
+__device__ __forceinline__ void sh_block_copy(float* tile, int stride, int col0, int width, int count, const float* src, float* dst, int lane,
+                                              unsigned rows = 0xffffffffu) {
 	const int total = count * width;
 	const uintptr_t addr = TO_SHARED ? reinterpret_cast<uintptr_t>(src) : reinterpret_cast<uintptr_t>(dst);
 	if ((addr & 15) == 0 && (total & 3) == 0) {
 		for (int e = lane * 4; e < total; e += 128) {
 			float vv[4];
 			if (TO_SHARED) {
+				if (!((rows >> (e / width)) & 1u) && !((rows >> ((e + 3) / width)) & 1u)) continue;
 				const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
 				vv[0] = v.x; vv[1] = v.y; vv[2] = v.z; vv[3] = v.w;
 			}
@@ -386,7 +399,7 @@ __device__ __forceinline__ void sh_block_copy(float* tile, int stride, int col0,
 	} else {
 		for (int e = lane; e < total; e += 32) {
 			const int r = e / width, c = e - r * width;
-			if (TO_SHARED) tile[r * stride + col0 + c] = __ldg(src + e);
+			if (TO_SHARED) { if ((rows >> r) & 1u) tile[r * stride + col0 + c] = __ldg(src + e); }
 			else dst[e] = tile[r * stride + col0 + c];
 		}
 	}
@@ -407,13 +420,22 @@ __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_kernel(int P, int D
 	// split layout (ABI 2): coefficient 0 comes from / goes to the [P,1,3] tensors, bands 1.. the [P,M-1,3] ones
 	const bool split = shs_rest != nullptr;
 	const int w0 = split ? 3 : row;
-	sh_block_copy<true>(tile, stride, 0, w0, count, shs + (size_t)g0 * w0, nullptr, lane);
-	if (split) sh_block_copy<true>(tile, stride, 3, row - 3, count, shs_rest + (size_t)g0 * (row - 3), nullptr, lane);
-	__syncwarp();
 	const int idx = g0 + lane;
+	// rows that need their coefficients: rendered AND a non-zero colour gradient after the clamp mask; for all others dL_dsh = 0 and
+	// the view-direction term vanishes, so their 12*M bytes are not read (occluded splats: a large share of a dense scene)
+	bool need = false;
+	if (lane < count && radii[idx] > 0) {
+		const uint8_t cb0 = clamped[idx];
+		const float* ga0 = grad_accum + (size_t)idx * GF + G_COL;
+		need = (!(cb0 & 1) && ga0[0] != 0.f) || (!(cb0 & 2) && ga0[1] != 0.f) || (!(cb0 & 4) && ga0[2] != 0.f);
+	}
+	const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+	sh_block_copy<true>(tile, stride, 0, w0, count, shs + (size_t)g0 * w0, nullptr, lane, need_mask);
+	if (split) sh_block_copy<true>(tile, stride, 3, row - 3, count, shs_rest + (size_t)g0 * (row - 3), nullptr, lane, need_mask);
+	__syncwarp();
 	if (lane < count) {
 		float* sh = tile + lane * stride;
-		if (!(radii[idx] > 0)) {
+		if (!need) {
 			for (int i = 0; i < row; i++) sh[i] = 0.f;
 		} else {
 			const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};

@@ -71,7 +71,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 template <bool COORD, bool DEPTH>
 __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float* __restrict__ records,
-    int W, int H, int grid_x, int row_begin, float focal_x, float focal_y, const float* __restrict__ bg_color,
+    int W, int H, int py_off, int Hs, int grid_x, int row_begin, float focal_x, float focal_y, const float* __restrict__ bg_color,
     const float* __restrict__ alphas, const float* __restrict__ normalmap, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ accum_depth, const float* __restrict__ accum_coord, const float* __restrict__ normal_length,
     const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_coords, const float* __restrict__ dL_dpixel_mcoords,
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 3 : 4)) render_backward_ker
 	const bool inside = px < W && py < H;
 	const float pxf = (float)px, pyf = (float)py;
 	const float wx0 = (float)bx0, wx1 = (float)min(bx0 + 7, W - 1), wy0 = (float)by0, wy1 = (float)min(by0 + 3, H - 1);
-	const int pix_id = W * py + px;
-	const size_t HW = (size_t)H * W;
+	const int pix_id = W * (py - py_off) + px;  // maps hold pixel rows [py_off, py_off + Hs)
+	const size_t HW = (size_t)Hs * W;
 
 	const uint2 range = ranges[tile_y * grid_x + tile_x];
 	const uint32_t* my_mask = hitmask + (size_t)chunk_base[tile_y * grid_x + tile_x] * 8 + warp;
@@ -362,7 +362,7 @@ static void launch_variant(const FwdParams& p, GeomView g, BinView b, ImgView im
 	static size_t configured[64] = {};
 	ensure_dynamic_smem(kern, smem, configured);
 	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
-	kern<<<grid, NTHREADS, smem, s>>>(img.ranges, b.point_list, g.records, p.W, p.H, p.grid_x, p.row_begin, p.focal_x, p.focal_y, p.background,
+	kern<<<grid, NTHREADS, smem, s>>>(img.ranges, b.point_list, g.records, p.W, p.H, p.py_off, p.Hs, p.grid_x, p.row_begin, p.focal_x, p.focal_y, p.background,
 	                                 gin.out_alpha, gin.out_normal, img.n_contrib, img.accum_depth, img.accum_coord, img.normal_length,
 	                                 gin.d_color, gin.d_coord, gin.d_mcoord, gin.d_depth, gin.d_mdepth, gin.d_alpha, gin.d_normal, grad_accum, img.chunk_base, b.hitmask);
 	count_launch();

@@ -23,7 +23,7 @@ namespace rgs {
 template <bool COORD, bool DEPTH>
 __global__ void __launch_bounds__(NTHREADS, (COORD ? 4 : 5)) render_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float* __restrict__ records,
-    int W, int H, int grid_x, int row_begin, float focal_x, float focal_y, const float* __restrict__ bg_color,
+    int W, int H, int py_off, int Hs, int grid_x, int row_begin, float focal_x, float focal_y, const float* __restrict__ bg_color,
     float* __restrict__ out_color, float* __restrict__ out_coord, float* __restrict__ out_mcoord, float* __restrict__ out_alpha,
     float* __restrict__ out_normal, float* __restrict__ out_depth, float* __restrict__ out_mdepth,
     uint32_t* __restrict__ n_contrib, float* __restrict__ accum_depth, float* __restrict__ accum_coord, float* __restrict__ normal_length,
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(NTHREADS, (COORD ? 4 : 5)) render_forward_kern
 		const float C[3] = {C01.x, C01.y, C2D.x};
 		const float Depth = C2D.y, weight = N2W.y;
 		const float Normal[3] = {N01.x, N01.y, N2W.x};
-		const int pix_id = W * py + px;
-		const size_t HW = (size_t)H * W;
+		const int pix_id = W * (py - py_off) + px;  // maps hold pixel rows [py_off, py_off + Hs): the whole image, or this call's slab
+		const size_t HW = (size_t)Hs * W;
 		n_contrib[pix_id] = last_contributor;
 		n_contrib[pix_id + HW] = max_contributor;
 #pragma unroll
@@ -218,7 +218,7 @@ static void launch_variant(const FwdParams& p, GeomView g, BinView b, ImgView im
 	static size_t configured[64] = {};
 	ensure_dynamic_smem(kern, smem, configured);
 	dim3 grid(p.grid_x, p.row_end - p.row_begin, 1);
-	kern<<<grid, NTHREADS, smem, s>>>(img.ranges, b.point_list, g.records, p.W, p.H, p.grid_x, p.row_begin, p.focal_x, p.focal_y, p.background,
+	kern<<<grid, NTHREADS, smem, s>>>(img.ranges, b.point_list, g.records, p.W, p.H, p.py_off, p.Hs, p.grid_x, p.row_begin, p.focal_x, p.focal_y, p.background,
 	                                 out.color, out.coord, out.mcoord, out.alpha, out.normal, out.depth, out.mdepth, img.n_contrib,
 	                                 img.accum_depth, img.accum_coord, img.normal_length, img.chunk_base, b.hitmask);
 	count_launch();

@@ -16,6 +16,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <algorithm>
 #include <string>
 #include <tuple>
 
@@ -67,7 +68,7 @@ struct CamHolder {
 void fill_camera(CamHolder& h, const torch::Tensor& like, const torch::Tensor& background, const torch::Tensor& viewmatrix,
                  const torch::Tensor& projmatrix, const torch::Tensor& campos, float tan_fovx, float tan_fovy, float kernel_size,
                  float scale_modifier, int H, int W, int degree, int M, bool prefiltered, bool require_coord, bool require_depth, bool debug,
-                 int row_begin, int row_end) {
+                 int row_begin, int row_end, bool compact = false) {
 	h.bg = as_input(background, like, "background");
 	h.view = as_input(viewmatrix, like, "viewmatrix");
 	h.proj = as_input(projmatrix, like, "projmatrix");
@@ -91,6 +92,7 @@ void fill_camera(CamHolder& h, const torch::Tensor& like, const torch::Tensor& b
 	c.debug = debug;
 	c.tile_row_begin = row_begin;
 	c.tile_row_end = row_end;
+	c.compact_slab = compact ? 1 : 0;
 }
 
 struct GaussHolder {
@@ -141,7 +143,7 @@ FwdResult forward_impl(const torch::Tensor& background, const torch::Tensor& mea
                        const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
                        const float kernel_size, const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
                        const torch::Tensor& campos, const bool prefiltered, const bool require_coord, const bool require_depth, const bool debug,
-                       int row_begin, int row_end, const torch::Tensor& sh_rest = torch::Tensor()) {
+                       int row_begin, int row_end, const torch::Tensor& sh_rest = torch::Tensor(), bool compact = false) {
 	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
 		AT_ERROR("means3D must have dimensions (num_points, 3)");
 	}
@@ -154,8 +156,11 @@ FwdResult forward_impl(const torch::Tensor& background, const torch::Tensor& mea
 	auto byte_opts = means3D.options().dtype(torch::kByte);
 	const int grid_y = (H + 15) / 16;
 	const bool whole = (row_begin == 0 && (row_end < 0 || row_end == grid_y));
-	const bool fill = (P == 0) || !whole;  // P == 0: the reference returns all-zero maps (rasterize_points.cu:90)
-	auto img = [&](int ch) { return fill ? torch::zeros({ch, H, W}, float_opts) : new_empty({ch, H, W}, float_opts); };
+	// compact: the maps hold the slab's pixel rows only ([ch, Hs, W]) and are fully written by the kernels
+	const int r1 = row_end < 0 ? grid_y : row_end;
+	const int Hm = compact ? std::max(0, std::min(r1 * 16, H) - row_begin * 16) : H;
+	const bool fill = (P == 0) || (!whole && !compact);  // P == 0: the reference returns all-zero maps (rasterize_points.cu:90)
+	auto img = [&](int ch) { return fill ? torch::zeros({ch, Hm, W}, float_opts) : new_empty({ch, Hm, W}, float_opts); };
 	torch::Tensor out_color = img(3), out_depth = img(1), out_mdepth = img(1), out_coord = img(3), out_mcoord = img(3), out_alpha = img(1),
 	              out_normal = img(3);
 	torch::Tensor radii = P == 0 ? torch::zeros({P}, int_opts) : new_empty({P}, int_opts);
@@ -166,7 +171,7 @@ FwdResult forward_impl(const torch::Tensor& background, const torch::Tensor& mea
 		const int M = sh_coeffs(sh, sh_rest);
 		CamHolder ch;
 		fill_camera(ch, means3D, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, kernel_size, scale_modifier, H, W, degree, M,
-		            prefiltered, require_coord, require_depth, debug, row_begin, row_end);
+		            prefiltered, require_coord, require_depth, debug, row_begin, row_end, compact);
 		GaussHolder gh;
 		fill_gaussians(gh, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp, sh_rest);
 		rgs_forward_out fo{out_color.data_ptr<float>(), out_coord.data_ptr<float>(), out_mcoord.data_ptr<float>(), out_alpha.data_ptr<float>(),
@@ -208,11 +213,14 @@ void fill_backward(BackwardCtx& c, const torch::Tensor& background, const torch:
                    const torch::Tensor& dL_dout_alpha, const torch::Tensor& dL_dout_normal, const torch::Tensor& normalmap, const torch::Tensor& sh,
                    const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
                    const torch::Tensor& imageBuffer, const torch::Tensor& alphas, const bool require_coord, const bool require_depth,
-                   const bool debug, int row_begin, int row_end, const torch::Tensor& sh_rest = torch::Tensor()) {
-	const int H = dL_dout_color.size(1), W = dL_dout_color.size(2);
+                   const bool debug, int row_begin, int row_end, const torch::Tensor& sh_rest = torch::Tensor(), bool compact = false,
+                   int image_height = -1) {
+	// the image height is read off the gradient map like the reference does (rasterize_points.cu:171-172), except for compact slab maps
+	const int H = (compact && image_height > 0) ? image_height : dL_dout_color.size(1), W = dL_dout_color.size(2);
+	TORCH_CHECK(!compact || image_height > 0, "compact slab maps need the full image height");
 	const int M = sh_coeffs(sh, sh_rest);
 	fill_camera(c.ch, means3D, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, kernel_size, scale_modifier, H, W, degree, M, false,
-	            require_coord, require_depth, debug, row_begin, row_end);
+	            require_coord, require_depth, debug, row_begin, row_end, compact);
 	torch::Tensor no_opacity = torch::empty({0});  // backward does not receive the opacities (rasterize_points.h:43-76)
 	fill_gaussians(c.gh, means3D, no_opacity, sh, colors, scales, rotations, cov3D_precomp, sh_rest);
 	c.g_color = as_input(dL_dout_color, means3D, "dL_dout_color");
@@ -380,10 +388,10 @@ FwdResult RasterizeGaussiansSlabCUDA(const torch::Tensor& background, const torc
                                      const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const float kernel_size,
                                      const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
                                      const torch::Tensor& campos, const bool prefiltered, const bool require_coord, const bool require_depth,
-                                     const bool debug, const int tile_row_begin, const int tile_row_end) {
+                                     const bool debug, const int tile_row_begin, const int tile_row_end, const bool compact) {
 	return forward_impl(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
 	                    tan_fovy, kernel_size, image_height, image_width, sh, degree, campos, prefiltered, require_coord, require_depth, debug,
-	                    tile_row_begin, tile_row_end);
+	                    tile_row_begin, tile_row_end, torch::Tensor(), compact);
 }
 
 // stage 1: returns the packed screen-space gradient accumulator [P, rgs_grad_stride] (additive across slabs)
@@ -396,7 +404,7 @@ torch::Tensor BackwardRenderCUDA(const torch::Tensor& background, const torch::T
                                  const torch::Tensor& normalmap, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
                                  const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
                                  const torch::Tensor& alphas, const bool require_coord, const bool require_depth, const bool debug,
-                                 const int tile_row_begin, const int tile_row_end) {
+                                 const int tile_row_begin, const int tile_row_end, const bool compact, const int image_height) {
 	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor: this rasterizer has no CPU path");
 	const c10::cuda::CUDAGuard guard(means3D.device());
 	const int P = means3D.size(0);
@@ -407,7 +415,7 @@ torch::Tensor BackwardRenderCUDA(const torch::Tensor& background, const torch::T
 		fill_backward(c, background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
 		              tan_fovy, kernel_size, dL_dout_color, dL_dout_coord, dL_dout_mcoord, dL_dout_depth, dL_dout_mdepth, dL_dout_alpha,
 		              dL_dout_normal, normalmap, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, alphas, require_coord, require_depth,
-		              debug, tile_row_begin, tile_row_end);
+		              debug, tile_row_begin, tile_row_end, torch::Tensor(), compact, image_height);
 		check(rgs_backward_render(&c.ch.cam, &c.gh.g, &c.in, acc.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()));
 	}
 	return acc;
@@ -431,6 +439,29 @@ void ExchangeConnect(const int64_t ex, const torch::Tensor& all_handles, const i
 	if (rgs_exchange_connect(reinterpret_cast<rgs_exchange*>(ex), h.data_ptr()) != RGS_OK) throw std::runtime_error(rgs_exchange_last_error());
 }
 
+// views of the exchange's persistent local accumulator / result rows, and the bare exchange step (self-check, tools)
+torch::Tensor ExchangeAccumulator(const int64_t ex, const int P, const int row_floats, const int device) {
+	return torch::from_blob(rgs_exchange_accumulator(reinterpret_cast<rgs_exchange*>(ex)), {P, row_floats},
+	                        torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCUDA, device));
+}
+
+torch::Tensor ExchangeResult(const int64_t ex, const int P, const int row_floats, const int device) {
+	return torch::from_blob(const_cast<float*>(rgs_exchange_result(reinterpret_cast<rgs_exchange*>(ex))), {P, row_floats},
+	                        torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCUDA, device));
+}
+
+void ExchangeRows(const int64_t ex, const torch::Tensor& tiles_touched, const torch::Tensor& radii) {
+	TORCH_CHECK(tiles_touched.is_cuda() && radii.is_cuda() && tiles_touched.scalar_type() == torch::kInt32 && radii.scalar_type() == torch::kInt32,
+	            "tiles_touched / radii must be CUDA int32 tensors");
+	const c10::cuda::CUDAGuard guard(radii.device());
+	torch::Tensor t = tiles_touched.contiguous(), r = radii.contiguous();
+	if (rgs_exchange_rows(reinterpret_cast<rgs_exchange*>(ex), (int)r.numel(), reinterpret_cast<const uint32_t*>(t.data_ptr<int>()), r.data_ptr<int>(),
+	                      at::cuda::getCurrentCUDAStream().stream()) != RGS_OK)
+		throw std::runtime_error(rgs_exchange_last_error());
+}
+
+int ExchangeStatus(const int64_t ex) { return rgs_exchange_status(reinterpret_cast<rgs_exchange*>(ex), at::cuda::getCurrentCUDAStream().stream()); }
+
 void ExchangeDestroy(const int64_t ex) { rgs_exchange_destroy(reinterpret_cast<rgs_exchange*>(ex)); }
 
 // stage 1 + exchange: same arguments as BackwardRenderCUDA after the handle; returns the SUMMED rows [P, stride] (a view
@@ -444,7 +475,8 @@ torch::Tensor BackwardRenderExchangeCUDA(const int64_t ex, const torch::Tensor& 
                                          const torch::Tensor& dL_dout_normal, const torch::Tensor& normalmap, const torch::Tensor& sh, const int degree,
                                          const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
                                          const torch::Tensor& imageBuffer, const torch::Tensor& alphas, const bool require_coord,
-                                         const bool require_depth, const bool debug, const int tile_row_begin, const int tile_row_end) {
+                                         const bool require_depth, const bool debug, const int tile_row_begin, const int tile_row_end,
+                                         const bool compact, const int image_height) {
 	TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor: this rasterizer has no CPU path");
 	const c10::cuda::CUDAGuard guard(means3D.device());
 	const int P = means3D.size(0);
@@ -456,7 +488,7 @@ torch::Tensor BackwardRenderExchangeCUDA(const int64_t ex, const torch::Tensor& 
 		fill_backward(c, background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
 		              tan_fovy, kernel_size, dL_dout_color, dL_dout_coord, dL_dout_mcoord, dL_dout_depth, dL_dout_mdepth, dL_dout_alpha,
 		              dL_dout_normal, normalmap, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, alphas, require_coord, require_depth,
-		              debug, tile_row_begin, tile_row_end);
+		              debug, tile_row_begin, tile_row_end, torch::Tensor(), compact, image_height);
 		check(rgs_backward_render_exchange(&c.ch.cam, &c.gh.g, &c.in, x, at::cuda::getCurrentCUDAStream().stream()));
 	}
 	return torch::from_blob(const_cast<float*>(rgs_exchange_result(x)), {P, GS}, means3D.options().dtype(torch::kFloat32));
@@ -688,13 +720,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
 	m.def("mark_visible", &markVisible);
 	// extras (not in the reference)
-	m.def("rasterize_gaussians_slab", &RasterizeGaussiansSlabCUDA);
-	m.def("rasterize_gaussians_backward_render", &BackwardRenderCUDA);
+	m.def("rasterize_gaussians_slab", &RasterizeGaussiansSlabCUDA, py::arg("background"), py::arg("means3D"), py::arg("colors"), py::arg("opacity"), py::arg("scales"), py::arg("rotations"), py::arg("scale_modifier"), py::arg("cov3D_precomp"), py::arg("viewmatrix"), py::arg("projmatrix"), py::arg("tan_fovx"), py::arg("tan_fovy"), py::arg("kernel_size"), py::arg("image_height"), py::arg("image_width"), py::arg("sh"), py::arg("degree"), py::arg("campos"), py::arg("prefiltered"), py::arg("require_coord"), py::arg("require_depth"), py::arg("debug"), py::arg("tile_row_begin"), py::arg("tile_row_end"), py::arg("compact") = false);
+	m.def("rasterize_gaussians_backward_render", &BackwardRenderCUDA, py::arg("background"), py::arg("means3D"), py::arg("radii"), py::arg("colors"), py::arg("scales"), py::arg("rotations"), py::arg("scale_modifier"), py::arg("cov3D_precomp"), py::arg("viewmatrix"), py::arg("projmatrix"), py::arg("tan_fovx"), py::arg("tan_fovy"), py::arg("kernel_size"), py::arg("dL_dout_color"), py::arg("dL_dout_coord"), py::arg("dL_dout_mcoord"), py::arg("dL_dout_depth"), py::arg("dL_dout_mdepth"), py::arg("dL_dout_alpha"), py::arg("dL_dout_normal"), py::arg("normalmap"), py::arg("sh"), py::arg("degree"), py::arg("campos"), py::arg("geomBuffer"), py::arg("R"), py::arg("binningBuffer"), py::arg("imageBuffer"), py::arg("alphas"), py::arg("require_coord"), py::arg("require_depth"), py::arg("debug"), py::arg("tile_row_begin"), py::arg("tile_row_end"), py::arg("compact") = false, py::arg("image_height") = -1);
 	m.def("rasterize_gaussians_backward_preprocess", &BackwardPreprocessCUDA);
 	m.def("exchange_create", &ExchangeCreate);
 	m.def("exchange_connect", &ExchangeConnect);
 	m.def("exchange_destroy", &ExchangeDestroy);
-	m.def("rasterize_gaussians_backward_render_exchange", &BackwardRenderExchangeCUDA);
+	m.def("exchange_accumulator", &ExchangeAccumulator);
+	m.def("exchange_result", &ExchangeResult);
+	m.def("exchange_rows", &ExchangeRows);
+	m.def("exchange_status", &ExchangeStatus);
+	m.def("rasterize_gaussians_backward_render_exchange", &BackwardRenderExchangeCUDA, py::arg("ex"), py::arg("background"), py::arg("means3D"), py::arg("radii"), py::arg("colors"), py::arg("scales"), py::arg("rotations"), py::arg("scale_modifier"), py::arg("cov3D_precomp"), py::arg("viewmatrix"), py::arg("projmatrix"), py::arg("tan_fovx"), py::arg("tan_fovy"), py::arg("kernel_size"), py::arg("dL_dout_color"), py::arg("dL_dout_coord"), py::arg("dL_dout_mcoord"), py::arg("dL_dout_depth"), py::arg("dL_dout_mdepth"), py::arg("dL_dout_alpha"), py::arg("dL_dout_normal"), py::arg("normalmap"), py::arg("sh"), py::arg("degree"), py::arg("campos"), py::arg("geomBuffer"), py::arg("R"), py::arg("binningBuffer"), py::arg("imageBuffer"), py::arg("alphas"), py::arg("require_coord"), py::arg("require_depth"), py::arg("debug"), py::arg("tile_row_begin"), py::arg("tile_row_end"), py::arg("compact") = false, py::arg("image_height") = -1);
 	m.def("rasterize_gaussians_split_sh", &RasterizeGaussiansSplitShCUDA);
 	m.def("rasterize_gaussians_backward_split_sh", &RasterizeGaussiansBackwardSplitShCUDA);
 	m.def("compute_3d_filter", &Compute3DFilter);

@@ -144,6 +144,55 @@ class GradExchange:
             dist.all_gather(gathered, mine, group=group)
             _C.exchange_connect(self._ex, torch.stack(gathered).cpu(), idx)
             dist.barrier(group=group)   # nobody pushes before every rank has mapped every window
+            why = self._self_check(_C, idx)
+            if why is not None:         # the same verdict on every rank (all-reduced): fall back together
+                import warnings
+                warnings.warn(f"peer gradient exchange failed its self-check ({why}); using the dense all-reduce")
+                self.fallback_reason = why
+                self.mode = "dense"
+
+    fallback_reason = None
+
+    def _self_check(self, C, idx):
+        """Two synthetic exchange steps with a known answer before the object is trusted: rank r touches every 3rd row starting at
+        (r + step) % 3 (+ row 0, touched by all) and fills it with f(step, rank, row); the result must be the sum over the ranks that
+        touched the row, bit for bit (small integers: exact in float), on every rank.  Returns None or the reason of the failure."""
+        P = min(self.capacity, 4096 + 17)
+        dev = torch.device("cuda", idx)
+        rows = torch.arange(P, device=dev)
+        radii = torch.ones(P, dtype=torch.int32, device=dev)
+        radii[5::11] = 0                                         # rows nobody renders are neither pushed nor spread
+        ok = True
+        try:
+            for step in (1, 2):
+                expect = torch.zeros(P, self.row_floats, device=dev)
+                mine = None
+                for r in range(self.world):
+                    touched = ((rows % 3) == ((r + step) % 3)) | (rows == 0)   # step 2 leaves some of step 1's rows untouched: they must read zero again
+                    touched &= radii > 0
+                    val = (touched.float() * (step * 64 + r + 1))[:, None] * (1 + (rows % 7).float())[:, None] * torch.ones(1, self.row_floats, device=dev)
+                    expect += val
+                    if r == self.rank:
+                        mine = (touched, val)
+                acc = C.exchange_accumulator(self._ex, P, self.row_floats, idx)
+                acc.copy_(mine[1])
+                C.exchange_rows(self._ex, mine[0].int(), radii)
+                if C.exchange_status(self._ex) != 0:
+                    ok = False
+                    break
+                got = C.exchange_result(self._ex, P, self.row_floats, idx)
+                vis = radii > 0
+                if not torch.equal(got[vis], expect[vis]) or bool(acc.any()):
+                    ok = False
+                    break
+        except Exception as e:   # noqa: BLE001  (a failing CUDA call: report, fall back)
+            ok = False
+            why_local = f"{type(e).__name__}: {e}"
+        flag = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            return None
+        return "a rank saw a wrong result or a barrier timeout" if ok else locals().get("why_local", "wrong result or barrier timeout on this rank")
 
     def backward_render(self, C, *stage1_args) -> torch.Tensor:
         """stage 1 (`rasterize_gaussians_backward_render` arguments) + exchange -> summed accumulator rows [P, row_floats]."""
@@ -173,13 +222,15 @@ class _ShardedRasterize(torch.autograd.Function):
     `_RasterizeGaussians` (reference: diff_gaussian_rasterization/__init__.py:44-169)."""
 
     @staticmethod
-    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, slab, group, exchange=None):
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, slab, group, exchange=None,
+                compact=False):
         from diff_gaussian_rasterization import _C
         s = raster_settings
         out = _C.rasterize_gaussians_slab(
             s.bg, means3D, colors_precomp, opacities, scales, rotations, s.scale_modifier, cov3Ds_precomp, s.viewmatrix, s.projmatrix,
             s.tanfovx, s.tanfovy, s.kernel_size, s.image_height, s.image_width, sh, s.sh_degree, s.campos, s.prefiltered,
-            s.require_coord, s.require_depth, s.debug, slab[0], slab[1])
+            s.require_coord, s.require_depth, s.debug, slab[0], slab[1], compact)
+        ctx.compact = compact
         num_rendered, color, coord, mcoord, alpha, normal, depth, mdepth, radii, geom, binning, img = out
         ctx.s, ctx.slab, ctx.group, ctx.num_rendered, ctx.exchange = s, slab, group, num_rendered, exchange
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, normal, radii, sh, geom, binning, img, alpha, opacities)
@@ -194,7 +245,7 @@ class _ShardedRasterize(torch.autograd.Function):
         stage1_args = (s.bg, means3D, radii, colors_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp, s.viewmatrix, s.projmatrix,
                        s.tanfovx, s.tanfovy, s.kernel_size, g_color, g_coord, g_mcoord, g_depth, g_mdepth, g_alpha, g_normal, normal, sh,
                        s.sh_degree, s.campos, geom, ctx.num_rendered, binning, img, alpha, s.require_coord, s.require_depth, s.debug,
-                       ctx.slab[0], ctx.slab[1])
+                       ctx.slab[0], ctx.slab[1], ctx.compact, s.image_height)
 
         def stage1():
             return _C.rasterize_gaussians_backward_render(*stage1_args)
@@ -209,7 +260,7 @@ class _ShardedRasterize(torch.autograd.Function):
             g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = stage2(ctx.exchange.backward_render(_C, *stage1_args))
         else:
             g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = backward_two_stage(stage1, stage2, ctx.group)
-        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, None, None, None, None
+        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, None, None, None, None, None
 
 
 class _GatherSlabs(torch.autograd.Function):
@@ -242,14 +293,15 @@ class _GatherSlabs(torch.autograd.Function):
 class ShardedGaussianRasterizer(torch.nn.Module):
     """`GaussianRasterizer` whose work is split by tile rows over the ranks of a process group.
 
-    Each rank returns full-size maps of which only its slab rows are filled (the rest is zero); callers that need
-    the whole image sum or gather the slabs (`gather_image`).  Gradients returned on every rank are the full,
+    Each rank returns full-size maps of which only its slab rows are filled (the rest is zero) or, with ``compact=True``, maps
+    that hold only the slab's pixel rows ([C, rows, W]); callers that need the whole image gather the slabs (`gather_image`).  Gradients returned on every rank are the full,
     already-reduced parameter gradients.
     """
 
     def __init__(self, raster_settings, rank: int | None = None, world_size: int | None = None, group=None, row_weights=None,
-                 exchange: GradExchange | None = None):
+                 exchange: GradExchange | None = None, compact: bool = False):
         super().__init__()
+        self.compact = compact     # True: the returned maps are [C, slab rows, W] (per-rank image memory and fill scale with 1/ranks)
         self.raster_settings = raster_settings
         self.group = group
         self.exchange = exchange   # a GradExchange created once by the caller (collective); None: one dense all-reduce per backward
@@ -270,7 +322,7 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         rotations = _absent() if rotations is None else rotations
         cov3D_precomp = _absent() if cov3D_precomp is None else cov3D_precomp
         return _ShardedRasterize.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                       self.raster_settings, self.slab, self.group, self.exchange)
+                                       self.raster_settings, self.slab, self.group, self.exchange, self.compact)
 
     def pixel_rows(self) -> Tuple[int, int]:
         H = self.raster_settings.image_height
@@ -285,6 +337,11 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         """
         H = self.raster_settings.image_height
         rows = [(min(b * TILE, H), min(e * TILE, H)) for b, e in self.slabs]
+        if self.compact:   # [C, slab rows, W] -> place into a full-size map first (the gather copies slab rows only)
+            full = img.new_zeros(img.shape[0], H, img.shape[2])
+            r0, r1 = rows[self.rank]
+            full[:, r0:r1] = img
+            img = full
         return _GatherSlabs.apply(img, self.group, rows, self.rank)
 
 

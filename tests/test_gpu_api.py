@@ -109,7 +109,8 @@ def test_c_abi_direct_call_with_raw_pointers():
                     ("kernel_size", ctypes.c_float), ("scale_modifier", ctypes.c_float), ("viewmatrix", ctypes.c_void_p),
                     ("projmatrix", ctypes.c_void_p), ("cam_pos", ctypes.c_void_p), ("background", ctypes.c_void_p), ("sh_degree", ctypes.c_int32),
                     ("sh_coeffs", ctypes.c_int32), ("require_coord", ctypes.c_int32), ("require_depth", ctypes.c_int32),
-                    ("prefiltered", ctypes.c_int32), ("debug", ctypes.c_int32), ("tile_row_begin", ctypes.c_int32), ("tile_row_end", ctypes.c_int32)]
+                    ("prefiltered", ctypes.c_int32), ("debug", ctypes.c_int32), ("tile_row_begin", ctypes.c_int32), ("tile_row_end", ctypes.c_int32),
+                    ("compact_slab", ctypes.c_int32)]
 
     class Gs(ctypes.Structure):
         _fields_ = [("P", ctypes.c_int32), ("means3D", ctypes.c_void_p), ("opacities", ctypes.c_void_p), ("shs", ctypes.c_void_p),
@@ -185,3 +186,39 @@ def test_sharded_rasterizer_single_rank_equals_plain():
         assert torch.equal(a, b)
     for k in l0:
         grad_close_gpu(l1[k].grad.cpu().numpy(), l0[k].grad.cpu().numpy(), k, rel=2e-4, elem=2e-4)
+
+
+def test_compact_slab_maps_equal_the_rows_of_the_whole_image():
+    """`compact` slab calls (multi-GPU: maps hold only the slab's pixel rows, [C, Hs, W]) against the whole-image call: forward
+    maps bit-identical to the corresponding rows, the slab accumulators add up to the whole-image accumulator (image height not a
+    multiple of 16, uneven slabs, all four variants)."""
+    from rade_gs_b200 import multigpu, scenes
+    C = _C()
+    sc = scenes.make_scene(30000, 200, 150, 260.0, -3.2, seed=8, view=scenes.look_at_view((0.2, 0.1, -0.3), (0.0, 0.0, 6.0)), bg=(0.3, 0.1, 0.2)).to(DEV)
+    g = scenes.make_upstream_grads(sc.height, sc.width, seed=9, device=DEV)
+    E = torch.Tensor([])
+    gy = (sc.height + 15) // 16
+    order = ("color", "coord", "mcoord", "depth", "mdepth", "alpha", "normal")
+
+    def fwd(b, e, compact):
+        return C.rasterize_gaussians_slab(sc.bg, sc.means3D, E, sc.opacities, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix, sc.projmatrix, sc.tanfovx,
+                                          sc.tanfovy, 0.1, sc.height, sc.width, sc.shs, 3, sc.campos, False, coord, depth, False, b, e, compact)
+
+    def bwd(out, grads, b, e, compact):
+        return C.rasterize_gaussians_backward_render(sc.bg, sc.means3D, out[8], E, sc.scales, sc.rotations, 1.0, E, sc.viewmatrix, sc.projmatrix, sc.tanfovx,
+                                                     sc.tanfovy, 0.1, *[grads[k] for k in order], out[5], sc.shs, 3, sc.campos, out[9], out[0], out[10],
+                                                     out[11], out[4], coord, depth, False, b, e, compact, sc.height)
+
+    for coord, depth in ((True, True), (False, True), (True, False), (False, False)):
+        whole = fwd(0, gy, False)
+        acc_whole = bwd(whole, g, 0, gy, False)
+        acc_sum = torch.zeros_like(acc_whole)
+        for b, e in multigpu.partition_tile_rows(gy, 3):
+            r0, r1 = b * 16, min(e * 16, sc.height)
+            out = fwd(b, e, True)
+            for i in range(1, 8):
+                assert out[i].shape[1] == r1 - r0 and torch.equal(out[i], whole[i][:, r0:r1]), (coord, depth, i, b, e)
+            assert torch.equal(out[8], whole[8])
+            acc_sum += bwd(out, {k: v[:, r0:r1].contiguous() for k, v in g.items()}, b, e, True)
+        rel = float((acc_sum - acc_whole).norm() / (acc_whole.norm() + 1e-30))
+        assert rel < 1e-5, (coord, depth, rel)

@@ -14,7 +14,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, outdir, exchange_mode, variant):
+def _worker(rank, world, port, outdir, exchange_mode, variant, compact=False):
     for p in (os.path.join(ROOT, "rade-gs_b200"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     import torch.distributed as dist
@@ -42,13 +42,16 @@ def _worker(rank, world, port, outdir, exchange_mode, variant):
             m2 = torch.zeros_like(lv["means3D"], requires_grad=True)
             color, radii, co, mco, dep, mdep, alpha, normal = rast(lv["means3D"], m2, lv["opacities"], shs=lv["shs"], scales=lv["scales"],
                                                                     rotations=lv["rotations"])
+            if color.shape[1] != sc.height:     # compact slab maps: the upstream gradients of this rank are the rows of its slab
+                r0, r1 = rast.pixel_rows()
+                g = {k: v[:, r0:r1] for k, v in g.items()}
             loss = (color * g["color"]).sum() + (dep * g["depth"]).sum() + (normal * g["normal"]).sum() + (alpha * g["alpha"]).sum() + \
                 (co * g["coord"]).sum() + (mdep * g["mdepth"]).sum() + (mco * g["mcoord"]).sum()
             loss.backward()
             return dict(color=color.detach(), depth=dep.detach(), normal=normal.detach(), coord=co.detach(), alpha=alpha.detach(), radii=radii,
                         **{"g_" + k: v.grad for k, v in lv.items()}, g_means2D=m2.grad)
 
-        sharded = ShardedGaussianRasterizer(st, exchange=ex)
+        sharded = ShardedGaussianRasterizer(st, exchange=ex, compact=compact)
         single = dgr.GaussianRasterizer(st)
         res = {}
         # three steps on the same exchange object: different upstream gradients, then fewer Gaussians (rows re-associated), so the
@@ -75,18 +78,18 @@ def _worker(rank, world, port, outdir, exchange_mode, variant):
 
 _WORLDS = [w for w in (2, 4, 8)]
 _VARIANTS = {"both_ks01": (True, True, 0.1), "depth_ks0": (False, True, 0.0), "coord_ks0": (True, False, 0.0)}
-_CASES = [(w, "peer", v) for w in _WORLDS for v in ("both_ks01",)] + [(2, "dense", "both_ks01"), (2, "peer", "depth_ks0"), (4, "peer", "coord_ks0"),
-                                                                      (8, "peer", "coord_ks0")]
+_CASES = [(w, "peer", v, False) for w in _WORLDS for v in ("both_ks01",)] + [(2, "dense", "both_ks01", False), (2, "peer", "depth_ks0", True),
+                                                                             (4, "peer", "coord_ks0", True), (8, "peer", "coord_ks0", True)]
 
 
-@pytest.mark.parametrize("world,exchange,variant", _CASES)
-def test_sharded_equals_single(world, exchange, variant, tmp_path):
+@pytest.mark.parametrize("world,exchange,variant,compact", _CASES)
+def test_sharded_equals_single(world, exchange, variant, compact, tmp_path):
     """`world` ranks against the single-GPU answer (computed on EVERY rank's GPU): images bit-exact, gradients within tolerance,
     and identical bits on all ranks."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000 + world, str(tmp_path), exchange, _VARIANTS[variant]), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000 + world, str(tmp_path), exchange, _VARIANTS[variant], compact), nprocs=world, join=True)
     for rank in range(world):
         res = np.load(tmp_path / f"res{rank}.npy", allow_pickle=True).item()
         for key, val in res.items():
