@@ -192,8 +192,9 @@ def test_compact_slab_maps_equal_the_rows_of_the_whole_image():
     """`compact` slab calls (multi-GPU: maps hold only the slab's pixel rows, [C, Hs, W]) against the whole-image call: forward
     maps bit-identical to the corresponding rows, the slab accumulators add up to the whole-image accumulator (image height not a
     multiple of 16, uneven slabs, all four variants)."""
+    import diff_gaussian_rasterization as dgr
     from rade_gs_b200 import multigpu, scenes
-    C = _C()
+    C = dgr._C
     sc = scenes.make_scene(30000, 200, 150, 260.0, -3.2, seed=8, view=scenes.look_at_view((0.2, 0.1, -0.3), (0.0, 0.0, 6.0)), bg=(0.3, 0.1, 0.2)).to(DEV)
     g = scenes.make_upstream_grads(sc.height, sc.width, seed=9, device=DEV)
     E = torch.Tensor([])
