@@ -459,7 +459,7 @@ def main():
             "impl": a.impl,
             "config": {"workload": f"{a.config}: {P} random-init Gaussians (SURVEY app. C seed 1234), {W}x{H}, SH deg 3, "
                                    f"require_depth={depth} require_coord={coord}, fwd+bwd at the _C boundary, num_rendered={R if not multi else 'per-slab'}",
-                       "parallelism": (f"tile-row slabs x{world}, gradient-row exchange: {exchange.mode}" + (f" (peer self-check failed: {exchange.fallback_reason})" if exchange.fallback_reason else "")
+                       "parallelism": (f"tile-row slabs x{world}, gradient-row exchange: {exchange.mode}" + (f" over {exchange.window}" if exchange.window else "") + (f" (peer self-check failed: {exchange.fallback_reason})" if exchange.fallback_reason else "")
                                        if multi else "single GPU"),
                        "l2": "per-step working set (192 MB SH + 248 MB SH grads + 64 MB records + sort buffers) exceeds the 126 MB L2; no explicit flush",
                        "protocol": f"median of {t_res['iterations']} per-iteration CUDA-event times ({t_res['windows']} windows of {a.steps} steps, barrier+synchronize around each window, max over ranks per iteration)"},

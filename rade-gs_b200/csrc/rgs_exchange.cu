@@ -36,6 +36,7 @@ struct PeerTable {
 	float* sum[MAX_WORLD];
 	float* full[MAX_WORLD];
 	uint32_t* flags[MAX_WORLD];
+	float* full_multicast;  // NVLS multicast mapping of every rank's `full` (one store reaches all ranks), or nullptr
 };
 
 }  // namespace rgs
@@ -49,6 +50,7 @@ struct rgs_exchange {
 	size_t bytes, off_full, off_flags;
 	char* peer_base[rgs::MAX_WORLD];
 	bool connected;
+	bool external;              // windows provided by the caller (rgs_exchange_attach): not opened / freed here
 	rgs::PeerTable tab;
 	float* acc_local;           // persistent local accumulator [capacity][row], kept all-zero between steps
 	uint8_t* dirty;             // [rows_per_rank_cap] owner-side: row was non-zero in `full` after the previous step
@@ -124,7 +126,14 @@ __global__ void __launch_bounds__(256) exchange_spread_kernel(int P, int rows_pe
 	__syncwarp(group);
 	if (nz) *src = make_float4(0.f, 0.f, 0.f, 0.f);
 	if (row_nz || was) {
-		for (int p = 0; p < world; p++) reinterpret_cast<float4*>(tab.full[p])[(size_t)idx * RQ + q] = v;
+		if (tab.full_multicast != nullptr) {
+			// one 16-byte store on the multicast mapping: the NVSwitch replicates it into every rank's window (this rank's included)
+			asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(tab.full_multicast + ((size_t)idx * RQ + q) * 4), "f"(v.x),
+			             "f"(v.y), "f"(v.z), "f"(v.w)
+			             : "memory");
+		} else {
+			for (int p = 0; p < world; p++) reinterpret_cast<float4*>(tab.full[p])[(size_t)idx * RQ + q] = v;
+		}
 		if (q == 0) dirty[local] = row_nz ? 1 : 0;
 	}
 }
@@ -144,6 +153,14 @@ using namespace rgs;
 	} while (0)
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static void layout(rgs_exchange* ex) {
+	const size_t row = (size_t)ex->row_floats * sizeof(float);
+	ex->rows_per_rank_cap = (ex->capacity + ex->world - 1) / ex->world;
+	ex->off_full = align_up((size_t)ex->rows_per_rank_cap * row, 256);
+	ex->off_flags = ex->off_full + align_up((size_t)ex->capacity * row, 256);
+	ex->bytes = ex->off_flags + 256;
+}
+
 
 extern "C" {
 
@@ -155,11 +172,8 @@ int32_t rgs_exchange_create(int32_t rank, int32_t world, int64_t capacity_rows, 
 	memset(ex, 0, sizeof(*ex));
 	ex->rank = rank; ex->world = world; ex->capacity = capacity_rows; ex->row_floats = row_floats;
 	RGS_X_TRY(cudaGetDevice(&ex->device));
-	ex->rows_per_rank_cap = (capacity_rows + world - 1) / world;
+	layout(ex);
 	const size_t row = (size_t)row_floats * sizeof(float);
-	ex->off_full = align_up((size_t)ex->rows_per_rank_cap * row, 256);
-	ex->off_flags = ex->off_full + align_up((size_t)capacity_rows * row, 256);
-	ex->bytes = ex->off_flags + 256;
 	RGS_X_TRY(cudaMalloc((void**)&ex->base, ex->bytes));
 	RGS_X_TRY(cudaMemset(ex->base, 0, ex->bytes));
 	RGS_X_TRY(cudaMalloc((void**)&ex->acc_local, (size_t)capacity_rows * row));
@@ -172,6 +186,49 @@ int32_t rgs_exchange_create(int32_t rank, int32_t world, int64_t capacity_rows, 
 	RGS_X_TRY(cudaIpcGetMemHandle(&h, ex->base));
 	memcpy(ipc_handle, &h, sizeof(h));
 	ex->last_P = -1;
+	*out = ex;
+	return RGS_OK;
+}
+
+size_t rgs_exchange_window_bytes(int32_t world, int64_t capacity_rows, int32_t row_floats) {
+	rgs_exchange tmp;
+	memset(&tmp, 0, sizeof(tmp));
+	tmp.world = world > 0 ? world : 1; tmp.capacity = capacity_rows; tmp.row_floats = row_floats;
+	layout(&tmp);
+	return tmp.bytes;
+}
+
+// Windows provided by the caller: window_ptrs[p] = this process's mapping of rank p's window (each rgs_exchange_window_bytes long,
+// ZERO-FILLED by the caller before any rank attaches), multicast_ptr = a multicast mapping of all of them or 0.  The product gets
+// both from torch's symmetric memory (cuMem VMM + NVLS multicast objects); the library only runs its kernels on the pointers.
+int32_t rgs_exchange_attach(int32_t rank, int32_t world, int64_t capacity_rows, int32_t row_floats, const uint64_t* window_ptrs,
+                            uint64_t multicast_ptr, rgs_exchange** out) {
+	if (!out || !window_ptrs) return xfail(RGS_E_INVALID, "null pointer");
+	if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return xfail(RGS_E_INVALID, "rank / world out of range (world <= 16)");
+	if (capacity_rows <= 0 || (row_floats != GRAD_FLOATS_BASE && row_floats != GRAD_FLOATS_COORD)) return xfail(RGS_E_INVALID, "capacity / row size");
+	rgs_exchange* ex = new rgs_exchange();
+	memset(ex, 0, sizeof(*ex));
+	ex->rank = rank; ex->world = world; ex->capacity = capacity_rows; ex->row_floats = row_floats;
+	RGS_X_TRY(cudaGetDevice(&ex->device));
+	layout(ex);
+	const size_t row = (size_t)row_floats * sizeof(float);
+	RGS_X_TRY(cudaMalloc((void**)&ex->acc_local, (size_t)capacity_rows * row));
+	RGS_X_TRY(cudaMemset(ex->acc_local, 0, (size_t)capacity_rows * row));
+	RGS_X_TRY(cudaMalloc((void**)&ex->dirty, (size_t)ex->rows_per_rank_cap));
+	RGS_X_TRY(cudaMemset(ex->dirty, 0, (size_t)ex->rows_per_rank_cap));
+	for (int p = 0; p < world; p++) {
+		ex->peer_base[p] = reinterpret_cast<char*>(window_ptrs[p]);
+		if (!ex->peer_base[p]) return xfail(RGS_E_INVALID, "null window pointer");
+		ex->tab.sum[p] = reinterpret_cast<float*>(ex->peer_base[p]);
+		ex->tab.full[p] = reinterpret_cast<float*>(ex->peer_base[p] + ex->off_full);
+		ex->tab.flags[p] = reinterpret_cast<uint32_t*>(ex->peer_base[p] + ex->off_flags);
+	}
+	ex->base = ex->peer_base[rank];
+	ex->tab.full_multicast = multicast_ptr ? reinterpret_cast<float*>(reinterpret_cast<char*>(multicast_ptr) + ex->off_full) : nullptr;
+	ex->external = true;
+	ex->connected = true;
+	ex->last_P = -1;
+	RGS_X_TRY(cudaDeviceSynchronize());
 	*out = ex;
 	return RGS_OK;
 }
@@ -200,10 +257,10 @@ int32_t rgs_exchange_connect(rgs_exchange* ex, const void* all_handles) {
 int32_t rgs_exchange_destroy(rgs_exchange* ex) {
 	if (!ex) return RGS_OK;
 	cudaDeviceSynchronize();
-	if (ex->connected)
+	if (ex->connected && !ex->external)
 		for (int p = 0; p < ex->world; p++)
 			if (p != ex->rank && ex->peer_base[p]) cudaIpcCloseMemHandle(ex->peer_base[p]);
-	cudaFree(ex->base);
+	if (!ex->external) cudaFree(ex->base);
 	cudaFree(ex->acc_local);
 	cudaFree(ex->dirty);
 	delete ex;

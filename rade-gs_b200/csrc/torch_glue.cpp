@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <string>
 #include <tuple>
+#include <vector>
 
 #include "rgs_b200.h"
 
@@ -432,6 +433,21 @@ std::tuple<int64_t, torch::Tensor> ExchangeCreate(const int rank, const int worl
 	return std::make_tuple((int64_t)reinterpret_cast<intptr_t>(ex), handle);
 }
 
+int64_t ExchangeWindowBytes(const int world, const int64_t capacity_rows, const int row_floats) {
+	return (int64_t)rgs_exchange_window_bytes(world, capacity_rows, row_floats);
+}
+
+int64_t ExchangeAttach(const int rank, const int world, const int64_t capacity_rows, const int row_floats, const std::vector<int64_t>& window_ptrs,
+                       const int64_t multicast_ptr, const int device) {
+	const c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, device));
+	TORCH_CHECK((int)window_ptrs.size() == world, "one window pointer per rank");
+	std::vector<uint64_t> ptrs(window_ptrs.begin(), window_ptrs.end());
+	rgs_exchange* ex = nullptr;
+	if (rgs_exchange_attach(rank, world, capacity_rows, row_floats, ptrs.data(), (uint64_t)multicast_ptr, &ex) != RGS_OK)
+		throw std::runtime_error(rgs_exchange_last_error());
+	return (int64_t)reinterpret_cast<intptr_t>(ex);
+}
+
 void ExchangeConnect(const int64_t ex, const torch::Tensor& all_handles, const int device) {
 	const c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, device));
 	torch::Tensor h = all_handles.to(torch::kCPU).contiguous();
@@ -725,6 +741,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 	m.def("rasterize_gaussians_backward_preprocess", &BackwardPreprocessCUDA);
 	m.def("exchange_create", &ExchangeCreate);
 	m.def("exchange_connect", &ExchangeConnect);
+	m.def("exchange_window_bytes", &ExchangeWindowBytes);
+	m.def("exchange_attach", &ExchangeAttach);
 	m.def("exchange_destroy", &ExchangeDestroy);
 	m.def("exchange_accumulator", &ExchangeAccumulator);
 	m.def("exchange_result", &ExchangeResult);

@@ -135,14 +135,26 @@ class GradExchange:
         if self.world == 1 or self.device.type != "cuda":
             mode = "dense"
         self.mode, self.capacity, self.row_floats, self._ex = mode, int(capacity_rows), int(row_floats), None
+        self.window = None
         if mode == "peer":
             from diff_gaussian_rasterization import _C
             idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-            self._ex, handle = _C.exchange_create(self.rank, self.world, self.capacity, self.row_floats, idx)
-            mine = handle.to(self.device)
-            gathered = [torch.empty_like(mine) for _ in range(self.world)]
-            dist.all_gather(gathered, mine, group=group)
-            _C.exchange_connect(self._ex, torch.stack(gathered).cpu(), idx)
+            if os.environ.get("RGS_EXCHANGE_WINDOW", "ipc") == "symm":
+                # opt-in: windows from torch's symmetric memory (cuMem VMM) with an NVLS multicast mapping -> the spread phase
+                # issues one store per 16 bytes and the NVSwitch replicates it; any failure falls back to the CUDA-IPC windows
+                try:
+                    self._attach_symmetric(_C, idx)
+                except Exception as e:  # noqa: BLE001
+                    import warnings
+                    warnings.warn(f"symmetric-memory windows unavailable ({type(e).__name__}: {e}); using CUDA IPC windows")
+                    self._ex = None
+            if self._ex is None:
+                self._ex, handle = _C.exchange_create(self.rank, self.world, self.capacity, self.row_floats, idx)
+                mine = handle.to(self.device)
+                gathered = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(gathered, mine, group=group)
+                _C.exchange_connect(self._ex, torch.stack(gathered).cpu(), idx)
+                self.window = "cuda-ipc"
             dist.barrier(group=group)   # nobody pushes before every rank has mapped every window
             why = self._self_check(_C, idx)
             if why is not None:         # the same verdict on every rank (all-reduced): fall back together
@@ -152,6 +164,20 @@ class GradExchange:
                 self.mode = "dense"
 
     fallback_reason = None
+
+    def _attach_symmetric(self, C, idx):
+        import torch.distributed._symmetric_memory as symm_mem
+        nbytes = int(C.exchange_window_bytes(self.world, self.capacity, self.row_floats))
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", idx))
+        g = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(buf, g.group_name)
+        buf.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+        self._ex = C.exchange_attach(self.rank, self.world, self.capacity, self.row_floats, [int(p) for p in hdl.buffer_ptrs], mc, idx)
+        self._symm = (buf, hdl)   # keep the allocation alive
+        self.window = "symmetric-memory" + (" + NVLS multicast" if mc else " (no multicast)")
 
     def _self_check(self, C, idx):
         """Two synthetic exchange steps with a known answer before the object is trusted: rank r touches every 3rd row starting at
