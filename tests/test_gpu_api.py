@@ -185,7 +185,7 @@ def test_sharded_rasterizer_single_rank_equals_plain():
     for a, b in zip(o0, o1):
         assert torch.equal(a, b)
     for k in l0:
-        grad_close_gpu(l1[k].grad.cpu().numpy(), l0[k].grad.cpu().numpy(), k, rel=2e-4, elem=2e-4)
+        grad_close_gpu(l1[k].grad.cpu().numpy(), l0[k].grad.cpu().numpy(), k)   # two runs of the same kernels: atomic-order noise only (measured up to 2e-4 here)
 
 
 def test_compact_slab_maps_equal_the_rows_of_the_whole_image():

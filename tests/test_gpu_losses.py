@@ -203,6 +203,7 @@ def test_row_range_ssim_kernels_add_up_to_the_whole_image():
     whole-image sums, and the per-range gradients (which reach 5 rows into the neighbouring ranges) add up to the whole gradient."""
     import diff_gaussian_rasterization as dgr
     C = dgr._C
+    DEV = "cuda:0"
     g = torch.Generator().manual_seed(17)
     H, W = 16 * 7 + 9, 150
     gt = torch.rand(3, H, W, generator=g).to(DEV)
