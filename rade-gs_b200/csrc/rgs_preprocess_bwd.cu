@@ -13,14 +13,15 @@
 //     RGS_FIX_MIP_GRADIENT to use the true opacity*coef instead (off by default: parity first);
 //   * gradients are w.r.t. the quaternion as given (no normalisation inside, backward.cu:554);
 //   * Sigma's eigen-decomposition follows the reference's solver and stopping rules (see rgs_geom.cuh).
+#include <string>
+
 #include "rgs_geom.cuh"
 
 namespace rgs {
 
-__global__ void __launch_bounds__(128, 4) preprocess_backward_kernel(FwdParams p, GeomView g, const int* __restrict__ radii,
-                                                                   const float* __restrict__ grad_accum, ParamGradOut out, int fix_mip) {
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= p.P) return;
+// One Gaussian's parameter gradients from its accumulator row.  Writes every output of the row (zeros when not rendered / nothing received).
+__device__ __forceinline__ void preprocess_backward_row(const FwdParams& p, const GeomView& g, const int* __restrict__ radii,
+                                                        const float* __restrict__ grad_accum, const ParamGradOut& out, int fix_mip, const int idx) {
 	bool visible = radii[idx] > 0;
 
 	float o_means2D[3] = {0, 0, 0}, o_colors[3] = {0, 0, 0}, o_opacity = 0.f, o_mean3D[3] = {0, 0, 0};
@@ -365,12 +366,125 @@ __global__ void __launch_bounds__(128, 4) preprocess_backward_kernel(FwdParams p
 	*reinterpret_cast<float4*>(out.d_rotations + 4 * idx) = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
 }
 
+// dense form: one thread per Gaussian (every output row written, zeros included)
+__global__ void __launch_bounds__(128, 4) preprocess_backward_kernel(FwdParams p, GeomView g, const int* __restrict__ radii,
+                                                                   const float* __restrict__ grad_accum, ParamGradOut out, int fix_mip) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= p.P) return;
+	preprocess_backward_row(p, g, radii, grad_accum, out, fix_mip, idx);
+}
+
+// compacted form: one thread per LISTED Gaussian (rendered and with a non-zero accumulator row); the outputs of all other rows were
+// zero-filled by the launcher.  In a dense scene most rendered splats are occluded in any one view (C2: 84 %, C3: 92 % of the
+// visible ones receive nothing), and a warp of the dense kernel runs the whole chain if ANY of its 32 rows needs it.
+__global__ void __launch_bounds__(128, 4) preprocess_backward_rows_kernel(FwdParams p, GeomView g, const int* __restrict__ radii,
+                                                                        const float* __restrict__ grad_accum, ParamGradOut out, int fix_mip,
+                                                                        const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
+	const int n = (int)*count;
+	for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x)
+		preprocess_backward_row(p, g, radii, grad_accum, out, fix_mip, (int)list[l]);
+}
+
+// rows that need work: rendered and any non-zero (or NaN) entry in the accumulator row.  One warp-aggregated atomic per warp.
+__global__ void __launch_bounds__(256) nonzero_rows_kernel(int P, const int* __restrict__ radii, const float* __restrict__ grad_accum, int GF,
+                                                            uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	bool nz = false;
+	if (idx < P && radii[idx] > 0) {
+		const float4* r = reinterpret_cast<const float4*>(grad_accum + (size_t)idx * GF);
+		for (int q = 0; q < GF / 4; q++) {
+			const float4 v = r[q];
+			nz = nz || !(v.x == 0.f) || !(v.y == 0.f) || !(v.z == 0.f) || !(v.w == 0.f);
+		}
+	}
+	const unsigned m = __ballot_sync(0xffffffffu, nz);
+	if (m == 0) return;
+	const int leader = __ffs(m) - 1;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if (nz) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)idx;
+}
+
 // ---- SH backward (backward.cu:21-140): warp-cooperative so the [M,3] rows move through shared memory coalesced ------
 // A warp owns 32 consecutive Gaussians = one contiguous 32*3M-float block of `shs` and of `dL_dsh`.  The block is
 // copied global -> shared with unit-stride 128-bit loads, each lane then works on its own row (row stride padded to
 // an odd number of floats: conflict-free), overwrites it in place with dL_dsh, and the block streams back coalesced.
 // The view-direction term is added to dL_dmeans3D (third part of the mean gradient, backward.cu:131-139).
 constexpr int SH_WARPS = 8;
+
+// SH backward of ONE Gaussian whose [M,3] coefficient row sits at `sh` (shared memory): the row is overwritten with dL_dsh and the
+// view-direction term is added to dL_dmeans3D (backward.cu:21-140).
+__device__ __forceinline__ void sh_backward_row(float* sh, int idx, int D, int M, const float* __restrict__ means3D, const float* __restrict__ cam_pos,
+                                                const uint8_t* __restrict__ clamped, const float* __restrict__ grad_accum, int GF,
+                                                float* __restrict__ d_means3D) {
+	const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+	const float3 campos = {cam_pos[0], cam_pos[1], cam_pos[2]};
+	const float3 dir_orig = {mean.x - campos.x, mean.y - campos.y, mean.z - campos.z};
+	const float dlen = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+	const float x = dir_orig.x / dlen, y = dir_orig.y / dlen, z = dir_orig.z / dlen;
+	const uint8_t cb = clamped[idx];
+	const float* ga = grad_accum + (size_t)idx * GF + G_COL;
+	const float dRGB[3] = {(cb & 1) ? 0.f : ga[0], (cb & 2) ? 0.f : ga[1], (cb & 4) ? 0.f : ga[2]};
+	const int deg = D;
+	float basis[16];
+	float ddx[16], ddy[16], ddz[16];  // d(basis_k)/d(dir)
+#pragma unroll
+	for (int k = 0; k < 16; k++) { basis[k] = 0.f; ddx[k] = 0.f; ddy[k] = 0.f; ddz[k] = 0.f; }
+	basis[0] = kSH0;
+	if (deg > 0) {
+		basis[1] = -kSH1 * y; basis[2] = kSH1 * z; basis[3] = -kSH1 * x;
+		ddx[3] = -kSH1; ddy[1] = -kSH1; ddz[2] = kSH1;
+		if (deg > 1) {
+			const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+			basis[4] = kSH2[0] * xy; basis[5] = kSH2[1] * yz; basis[6] = kSH2[2] * (2.f * zz - xx - yy);
+			basis[7] = kSH2[3] * xz; basis[8] = kSH2[4] * (xx - yy);
+			ddx[4] = kSH2[0] * y; ddx[6] = kSH2[2] * 2.f * -x; ddx[7] = kSH2[3] * z; ddx[8] = kSH2[4] * 2.f * x;
+			ddy[4] = kSH2[0] * x; ddy[5] = kSH2[1] * z; ddy[6] = kSH2[2] * 2.f * -y; ddy[8] = kSH2[4] * 2.f * -y;
+			ddz[5] = kSH2[1] * y; ddz[6] = kSH2[2] * 2.f * 2.f * z; ddz[7] = kSH2[3] * x;
+			if (deg > 2) {
+				basis[9] = kSH3[0] * y * (3.f * xx - yy); basis[10] = kSH3[1] * xy * z;
+				basis[11] = kSH3[2] * y * (4.f * zz - xx - yy); basis[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+				basis[13] = kSH3[4] * x * (4.f * zz - xx - yy); basis[14] = kSH3[5] * z * (xx - yy);
+				basis[15] = kSH3[6] * x * (xx - 3.f * yy);
+				ddx[9] = kSH3[0] * 3.f * 2.f * xy; ddx[10] = kSH3[1] * yz; ddx[11] = kSH3[2] * -2.f * xy; ddx[12] = kSH3[3] * -3.f * 2.f * xz;
+				ddx[13] = kSH3[4] * (-3.f * xx + 4.f * zz - yy); ddx[14] = kSH3[5] * 2.f * xz; ddx[15] = kSH3[6] * 3.f * (xx - yy);
+				ddy[9] = kSH3[0] * 3.f * (xx - yy); ddy[10] = kSH3[1] * xz; ddy[11] = kSH3[2] * (-3.f * yy + 4.f * zz - xx);
+				ddy[12] = kSH3[3] * -3.f * 2.f * yz; ddy[13] = kSH3[4] * -2.f * xy; ddy[14] = kSH3[5] * -2.f * yz; ddy[15] = kSH3[6] * -3.f * 2.f * xy;
+				ddz[10] = kSH3[1] * xy; ddz[11] = kSH3[2] * 4.f * 2.f * yz; ddz[12] = kSH3[3] * 3.f * (2.f * zz - xx - yy);
+				ddz[13] = kSH3[4] * 4.f * 2.f * xz; ddz[14] = kSH3[5] * (xx - yy);
+			}
+		}
+	}
+	const int ncoef = (deg + 1) * (deg + 1);
+	float3 dL_ddir = {0.f, 0.f, 0.f};
+#pragma unroll
+	for (int k = 0; k < 16; k++) {
+		if (k < M) {
+			float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+			if (k < ncoef) {
+				o0 = basis[k] * dRGB[0]; o1 = basis[k] * dRGB[1]; o2 = basis[k] * dRGB[2];
+				if (k > 0) {
+					const float sd = sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2];
+					dL_ddir.x += ddx[k] * sd;
+					dL_ddir.y += ddy[k] * sd;
+					dL_ddir.z += ddz[k] * sd;
+				}
+			}
+			sh[3 * k] = o0; sh[3 * k + 1] = o1; sh[3 * k + 2] = o2;
+		}
+	}
+	// through the normalisation of the view direction (auxiliary.h:123-133)
+	const float sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;
+	const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
+	float* dm = d_means3D + 3 * idx;
+	dm[0] += ((+sum2 - dir_orig.x * dir_orig.x) * dL_ddir.x - dir_orig.y * dir_orig.x * dL_ddir.y - dir_orig.z * dir_orig.x * dL_ddir.z) * invsum32;
+	dm[1] += (-dir_orig.x * dir_orig.y * dL_ddir.x + (sum2 - dir_orig.y * dir_orig.y) * dL_ddir.y - dir_orig.z * dir_orig.y * dL_ddir.z) * invsum32;
+	dm[2] += (-dir_orig.x * dir_orig.z * dL_ddir.x - dir_orig.y * dir_orig.z * dL_ddir.y + (sum2 - dir_orig.z * dir_orig.z) * dL_ddir.z) * invsum32;
+}
+
+
 
 // `count` rows of `width` floats, contiguous in global memory, <-> columns [col0, col0 + width) of the padded shared tile
 // `rows` (loads only): bit r set = row r is wanted; the 16-byte chunks of the other rows are not fetched (their slots are
@@ -438,69 +552,7 @@ __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_kernel(int P, int D
 		if (!need) {
 			for (int i = 0; i < row; i++) sh[i] = 0.f;
 		} else {
-			const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
-			const float3 campos = {cam_pos[0], cam_pos[1], cam_pos[2]};
-			const float3 dir_orig = {mean.x - campos.x, mean.y - campos.y, mean.z - campos.z};
-			const float dlen = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-			const float x = dir_orig.x / dlen, y = dir_orig.y / dlen, z = dir_orig.z / dlen;
-			const uint8_t cb = clamped[idx];
-			const float* ga = grad_accum + (size_t)idx * GF + G_COL;
-			const float dRGB[3] = {(cb & 1) ? 0.f : ga[0], (cb & 2) ? 0.f : ga[1], (cb & 4) ? 0.f : ga[2]};
-			const int deg = D;
-			float basis[16];
-			float ddx[16], ddy[16], ddz[16];  // d(basis_k)/d(dir)
-#pragma unroll
-			for (int k = 0; k < 16; k++) { basis[k] = 0.f; ddx[k] = 0.f; ddy[k] = 0.f; ddz[k] = 0.f; }
-			basis[0] = kSH0;
-			if (deg > 0) {
-				basis[1] = -kSH1 * y; basis[2] = kSH1 * z; basis[3] = -kSH1 * x;
-				ddx[3] = -kSH1; ddy[1] = -kSH1; ddz[2] = kSH1;
-				if (deg > 1) {
-					const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-					basis[4] = kSH2[0] * xy; basis[5] = kSH2[1] * yz; basis[6] = kSH2[2] * (2.f * zz - xx - yy);
-					basis[7] = kSH2[3] * xz; basis[8] = kSH2[4] * (xx - yy);
-					ddx[4] = kSH2[0] * y; ddx[6] = kSH2[2] * 2.f * -x; ddx[7] = kSH2[3] * z; ddx[8] = kSH2[4] * 2.f * x;
-					ddy[4] = kSH2[0] * x; ddy[5] = kSH2[1] * z; ddy[6] = kSH2[2] * 2.f * -y; ddy[8] = kSH2[4] * 2.f * -y;
-					ddz[5] = kSH2[1] * y; ddz[6] = kSH2[2] * 2.f * 2.f * z; ddz[7] = kSH2[3] * x;
-					if (deg > 2) {
-						basis[9] = kSH3[0] * y * (3.f * xx - yy); basis[10] = kSH3[1] * xy * z;
-						basis[11] = kSH3[2] * y * (4.f * zz - xx - yy); basis[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-						basis[13] = kSH3[4] * x * (4.f * zz - xx - yy); basis[14] = kSH3[5] * z * (xx - yy);
-						basis[15] = kSH3[6] * x * (xx - 3.f * yy);
-						ddx[9] = kSH3[0] * 3.f * 2.f * xy; ddx[10] = kSH3[1] * yz; ddx[11] = kSH3[2] * -2.f * xy; ddx[12] = kSH3[3] * -3.f * 2.f * xz;
-						ddx[13] = kSH3[4] * (-3.f * xx + 4.f * zz - yy); ddx[14] = kSH3[5] * 2.f * xz; ddx[15] = kSH3[6] * 3.f * (xx - yy);
-						ddy[9] = kSH3[0] * 3.f * (xx - yy); ddy[10] = kSH3[1] * xz; ddy[11] = kSH3[2] * (-3.f * yy + 4.f * zz - xx);
-						ddy[12] = kSH3[3] * -3.f * 2.f * yz; ddy[13] = kSH3[4] * -2.f * xy; ddy[14] = kSH3[5] * -2.f * yz; ddy[15] = kSH3[6] * -3.f * 2.f * xy;
-						ddz[10] = kSH3[1] * xy; ddz[11] = kSH3[2] * 4.f * 2.f * yz; ddz[12] = kSH3[3] * 3.f * (2.f * zz - xx - yy);
-						ddz[13] = kSH3[4] * 4.f * 2.f * xz; ddz[14] = kSH3[5] * (xx - yy);
-					}
-				}
-			}
-			const int ncoef = (deg + 1) * (deg + 1);
-			float3 dL_ddir = {0.f, 0.f, 0.f};
-#pragma unroll
-			for (int k = 0; k < 16; k++) {
-				if (k < M) {
-					float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-					if (k < ncoef) {
-						o0 = basis[k] * dRGB[0]; o1 = basis[k] * dRGB[1]; o2 = basis[k] * dRGB[2];
-						if (k > 0) {
-							const float sd = sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2];
-							dL_ddir.x += ddx[k] * sd;
-							dL_ddir.y += ddy[k] * sd;
-							dL_ddir.z += ddz[k] * sd;
-						}
-					}
-					sh[3 * k] = o0; sh[3 * k + 1] = o1; sh[3 * k + 2] = o2;
-				}
-			}
-			// through the normalisation of the view direction (auxiliary.h:123-133)
-			const float sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;
-			const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
-			float* dm = d_means3D + 3 * idx;
-			dm[0] += ((+sum2 - dir_orig.x * dir_orig.x) * dL_ddir.x - dir_orig.y * dir_orig.x * dL_ddir.y - dir_orig.z * dir_orig.x * dL_ddir.z) * invsum32;
-			dm[1] += (-dir_orig.x * dir_orig.y * dL_ddir.x + (sum2 - dir_orig.y * dir_orig.y) * dL_ddir.y - dir_orig.z * dir_orig.y * dL_ddir.z) * invsum32;
-			dm[2] += (-dir_orig.x * dir_orig.z * dL_ddir.x - dir_orig.y * dir_orig.z * dL_ddir.y + (sum2 - dir_orig.z * dir_orig.z) * dL_ddir.z) * invsum32;
+			sh_backward_row(sh, idx, D, M, means3D, cam_pos, clamped, grad_accum, GF, d_means3D);
 		}
 	}
 	__syncwarp();
@@ -508,19 +560,111 @@ __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_kernel(int P, int D
 	if (split) sh_block_copy<false>(tile, stride, 3, row - 3, count, nullptr, d_sh_rest + (size_t)g0 * (row - 3), lane);
 }
 
+// compacted form of the SH backward: a warp takes 32 LISTED Gaussians, gathers their coefficient rows (12*M contiguous bytes each)
+// into shared memory, lane = row as above, and scatters the dL_dsh rows back; all other rows of dL_dsh were zero-filled.
+__global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_rows_kernel(int D, int M, const float* __restrict__ means3D, const float* __restrict__ cam_pos,
+                                                                          const float* __restrict__ shs, const float* __restrict__ shs_rest,
+                                                                          const uint8_t* __restrict__ clamped, const float* __restrict__ grad_accum, int GF,
+                                                                          float* __restrict__ d_sh, float* __restrict__ d_sh_rest,
+                                                                          float* __restrict__ d_means3D, const uint32_t* __restrict__ list,
+                                                                          const uint32_t* __restrict__ count) {
+	extern __shared__ float s_sh[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int row = 3 * M, stride = row | 1;
+	float* tile = s_sh + (size_t)warp * 32 * stride;
+	const bool split = shs_rest != nullptr;
+	const int n = (int)*count;
+	for (int l0 = (blockIdx.x * SH_WARPS + warp) * 32; l0 < n; l0 += gridDim.x * SH_WARPS * 32) {
+		const int mine = (l0 + lane < n) ? (int)list[l0 + lane] : -1;
+		bool need = false;  // a zero colour gradient (after the clamp mask) leaves dL_dsh = 0 and no view-direction term
+		if (mine >= 0) {
+			const uint8_t cb = clamped[mine];
+			const float* ga = grad_accum + (size_t)mine * GF + G_COL;
+			need = (!(cb & 1) && !(ga[0] == 0.f)) || (!(cb & 2) && !(ga[1] == 0.f)) || (!(cb & 4) && !(ga[2] == 0.f));
+		}
+		const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+		for (unsigned m = need_mask; m; m &= m - 1) {
+			const int r = __ffs(m) - 1;
+			const int rid = __shfl_sync(0xffffffffu, mine, r);
+			float* dst = tile + r * stride;
+			if (!split) {
+				const float* src = shs + (size_t)rid * row;
+				for (int e = lane; e < row; e += 32) dst[e] = __ldg(src + e);
+			} else {
+				if (lane < 3) dst[lane] = __ldg(shs + (size_t)rid * 3 + lane);
+				const float* src = shs_rest + (size_t)rid * (row - 3);
+				for (int e = lane; e < row - 3; e += 32) dst[3 + e] = __ldg(src + e);
+			}
+		}
+		__syncwarp();
+		if (need) sh_backward_row(tile + lane * stride, mine, D, M, means3D, cam_pos, clamped, grad_accum, GF, d_means3D);
+		__syncwarp();
+		for (unsigned m = need_mask; m; m &= m - 1) {
+			const int r = __ffs(m) - 1;
+			const int rid = __shfl_sync(0xffffffffu, mine, r);
+			const float* src = tile + r * stride;
+			if (!split) {
+				float* dst = d_sh + (size_t)rid * row;
+				for (int e = lane; e < row; e += 32) dst[e] = src[e];
+			} else {
+				if (lane < 3) d_sh[(size_t)rid * 3 + lane] = src[lane];
+				float* dst = d_sh_rest + (size_t)rid * (row - 3);
+				for (int e = lane; e < row - 3; e += 32) dst[e] = src[3 + e];
+			}
+		}
+		__syncwarp();
+	}
+}
+
 void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s) {
 	static const int fix_mip = getenv("RGS_FIX_MIP_GRADIENT") != nullptr && atoi(getenv("RGS_FIX_MIP_GRADIENT")) != 0;
-	preprocess_backward_kernel<<<(p.P + 127) / 128, 128, 0, s>>>(p, g, radii, grad_accum, out, fix_mip);
-	count_launch();
-	if (p.shs != nullptr && out.d_sh != nullptr && p.M > 0) {
-		const int stride = (3 * p.M) | 1;
-		const size_t smem = (size_t)SH_WARPS * 32 * stride * sizeof(float);
-		static size_t configured[64] = {};
-		if (smem > 48 * 1024) ensure_dynamic_smem(sh_backward_kernel, smem, configured);
-		const int per_block = SH_WARPS * 32;
-		sh_backward_kernel<<<(p.P + per_block - 1) / per_block, per_block, smem, s>>>(p.P, p.D, p.M, p.means3D, p.cam_pos, p.shs, p.shs_rest, radii,
-		                                                                               g.clamped, grad_accum, grad_floats(p.coord), out.d_sh, out.d_sh_rest,
-		                                                                               out.d_means3D);
+	static const bool dense = getenv("RGS_BWD_PREPROCESS") != nullptr && std::string(getenv("RGS_BWD_PREPROCESS")) == "dense";
+	const bool has_sh = p.shs != nullptr && out.d_sh != nullptr && p.M > 0;
+	const int stride = (3 * p.M) | 1;
+	const size_t smem = (size_t)SH_WARPS * 32 * stride * sizeof(float);
+	static size_t configured[64] = {}, configured_rows[64] = {};
+	if (dense || g.scan_temp == nullptr || g.scan_temp_bytes < sizeof(uint32_t)) {
+		// every row through the full chain (kept as a cross-check: RGS_BWD_PREPROCESS=dense)
+		preprocess_backward_kernel<<<(p.P + 127) / 128, 128, 0, s>>>(p, g, radii, grad_accum, out, fix_mip);
+		count_launch();
+		if (has_sh) {
+			if (smem > 48 * 1024) ensure_dynamic_smem(sh_backward_kernel, smem, configured);
+			const int per_block = SH_WARPS * 32;
+			sh_backward_kernel<<<(p.P + per_block - 1) / per_block, per_block, smem, s>>>(p.P, p.D, p.M, p.means3D, p.cam_pos, p.shs, p.shs_rest, radii,
+			                                                                               g.clamped, grad_accum, grad_floats(p.coord), out.d_sh,
+			                                                                               out.d_sh_rest, out.d_means3D);
+			count_launch();
+		}
+		return;
+	}
+	// compacted: zero-fill the outputs (memsets run at HBM write speed), list the rows that received anything, run the chains on those.
+	// The list lives in the geometry buffer's `offsets` array (only the cross-check radix path of forward uses it), its length in the
+	// first word of the scan scratch.
+	const size_t P = (size_t)p.P;
+	const bool split = p.shs_rest != nullptr;
+	cudaMemsetAsync(out.d_means2D, 0, P * 3 * sizeof(float), s);
+	cudaMemsetAsync(out.d_colors, 0, P * 3 * sizeof(float), s);
+	cudaMemsetAsync(out.d_opacity, 0, P * sizeof(float), s);
+	cudaMemsetAsync(out.d_means3D, 0, P * 3 * sizeof(float), s);
+	cudaMemsetAsync(out.d_cov3D, 0, P * 6 * sizeof(float), s);
+	cudaMemsetAsync(out.d_scales, 0, P * 3 * sizeof(float), s);
+	cudaMemsetAsync(out.d_rotations, 0, P * 4 * sizeof(float), s);
+	if (has_sh) {
+		cudaMemsetAsync(out.d_sh, 0, P * (split ? 3 : 3 * p.M) * sizeof(float), s);
+		if (split && out.d_sh_rest != nullptr) cudaMemsetAsync(out.d_sh_rest, 0, P * (3 * p.M - 3) * sizeof(float), s);
+	}
+	uint32_t* list = g.offsets;
+	uint32_t* count = reinterpret_cast<uint32_t*>(g.scan_temp);
+	cudaMemsetAsync(count, 0, sizeof(uint32_t), s);
+	const int GF = grad_floats(p.coord);
+	nonzero_rows_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p.P, radii, grad_accum, GF, list, count);
+	const int sms = 148;
+	preprocess_backward_rows_kernel<<<sms * 4, 128, 0, s>>>(p, g, radii, grad_accum, out, fix_mip, list, count);
+	count_launch(2 + 8 + (has_sh ? 1 : 0));
+	if (has_sh) {
+		if (smem > 48 * 1024) ensure_dynamic_smem(sh_backward_rows_kernel, smem, configured_rows);
+		sh_backward_rows_kernel<<<sms * 2, SH_WARPS * 32, smem, s>>>(p.D, p.M, p.means3D, p.cam_pos, p.shs, p.shs_rest, g.clamped, grad_accum, GF, out.d_sh,
+		                                                            out.d_sh_rest, out.d_means3D, list, count);
 		count_launch();
 	}
 }

@@ -6,8 +6,8 @@ byte-identical copies under oracle/_ref/refsrc/ (git-ignored, shipped like the r
 this image lacks (plyfile, simple_knn, trimesh, open3d, matplotlib) are satisfied by tests/ref_stubs/.  Skipped only when the
 staged copy is absent.
   1. a tiny Blender-format dataset is rendered with this rasterizer (known Gaussians, 10 cameras on a ring);
-  2. `python train.py -s <data> -m <out> --iterations 60 ...` (densification, opacity reset, depth-normal regularisation and
-     the 3D filter all switched on early) must run to completion, save a PLY and report a PSNR;
+  2. `python train.py -s <data> -m <out> --iterations 60 ...` (densification at 20 / 40, depth-normal regularisation from 20, opacity
+     reset at 45, the 3D filter recomputed after every densification) must run to completion, save a PLY and report a PSNR;
   3. `python render.py -m <out>` must write the renders;
   4. `gaussian_renderer.render()` on the trained model must return exactly the bits of a raw `_C.rasterize_gaussians` call on
      the same activated tensors, for the depth and the coordinate-map variant.
@@ -130,8 +130,10 @@ def trained(tmp_path_factory):
     data, out = str(root / "data"), str(root / "out")
     _make_dataset(data)
     cmd = [sys.executable, os.path.join(REFSRC, "train.py"), "-s", data, "-m", out, "--iterations", "60", "--test_iterations", "60",
-           "--save_iterations", "60", "--checkpoint_iterations", "60", "--densify_from_iter", "10", "--densification_interval", "15",
-           "--opacity_reset_interval", "40", "--regularization_from_iter", "20", "--eval"]
+           "--save_iterations", "60", "--checkpoint_iterations", "60", "--densify_from_iter", "10", "--densification_interval", "20",
+           "--densify_until_iter", "50", "--opacity_reset_interval", "45", "--regularization_from_iter", "20", "--eval"]
+    # schedule: densify + prune at 20 and 40, depth-normal regularisation from 20, opacity reset at 45, no pruning after the reset (the
+    # reference's compute_3D_filter fails on an EMPTY model -- gaussian_model.py:227 -- which a prune right after a reset produces)
     r = subprocess.run(cmd, cwd=REFSRC, env=_env(), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, "train.py failed:\n" + r.stdout[-3000:] + "\n" + r.stderr[-3000:]
     return data, out, r.stdout
@@ -146,7 +148,7 @@ def test_reference_train_py_runs_unchanged(trained):
     m = re.search(r"\[ITER 60\] Evaluating train: L1 ([0-9.eE+-]+) PSNR ([0-9.eE+-]+)", log)
     assert m, log[-2000:]
     l1, psnr = float(m.group(1)), float(m.group(2))
-    assert math.isfinite(l1) and math.isfinite(psnr) and psnr > 10.0, (l1, psnr)   # 60 iterations from a random cloud: a sanity bar, not a quality claim
+    assert math.isfinite(l1) and math.isfinite(psnr) and psnr > 5.0, (l1, psnr)   # 60 iterations from a random cloud, opacities reset at 45: a sanity bar, not a quality claim
 
 
 def test_reference_render_py_runs_unchanged(trained):
