@@ -9,6 +9,7 @@
 //       sum  [rows_per_rank][row]   reduce target of the rows it owns
 //       full [capacity][row]        the summed rows of ALL Gaussians, as backward-preprocess reads them
 //       flags[world]                barrier epochs written by the peers
+//       mark [rows_per_rank]        one byte per owned row: somebody pushed into it this step
 //   1. push   : a rank walks the rows its slab touched (tiles_touched > 0), adds each non-zero row into the OWNER's `sum`
 //               with 16-byte vector reductions straight through NVLink (red.global.add.v4.f32 on the peer mapping), and
 //               clears its local row (the local accumulator is persistent: no 64..384 MB memset per step);
@@ -36,6 +37,7 @@ struct PeerTable {
 	float* sum[MAX_WORLD];
 	float* full[MAX_WORLD];
 	uint32_t* flags[MAX_WORLD];
+	uint8_t* mark[MAX_WORLD];  // [rows_per_rank_cap] per owned row: some rank pushed into it this step
 	float* full_multicast;  // NVLS multicast mapping of every rank's `full` (one store reaches all ranks), or nullptr
 };
 
@@ -47,7 +49,7 @@ struct rgs_exchange {
 	int row_floats;
 	int64_t rows_per_rank_cap;
 	char* base;                 // own window
-	size_t bytes, off_full, off_flags;
+	size_t bytes, off_full, off_flags, off_mark;
 	char* peer_base[rgs::MAX_WORLD];
 	bool connected;
 	bool external;              // windows provided by the caller (rgs_exchange_attach): not opened / freed here
@@ -64,21 +66,38 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// one thread per 16 bytes of a row; RQ = float4 per row (4 or 8)
+// One thread per Gaussian finds the rows this rank's slab touched (coalesced read of the per-splat tile counts); the rows found by a
+// warp are then handled one after the other by its first RQ lanes (RQ = float4 per row, 4 or 8): read the local row, clear it
+// (self-cleaning accumulator), add the non-zero quarters into the OWNER's `sum` row over NVLink and raise the owner's per-row mark so
+// that its spread pass looks at this row.  (A thread per 16 bytes, as first written, made the kernel thread-count bound: 0.4-0.5 ms at
+// 3-10 M Gaussians although only a few per cent of the rows carry anything.)
 template <int RQ>
 __global__ void __launch_bounds__(256) exchange_push_kernel(int P, int rows_per_rank, float4* __restrict__ acc_local,
                                                             const uint32_t* __restrict__ tiles_touched, PeerTable tab) {
-	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const int idx = (int)(t / RQ), q = (int)(t % RQ);
-	if (idx >= P) return;
-	if (tiles_touched[idx] == 0) return;  // nothing of this splat in my slab: my row is (and stays) zero
-	float4* src = acc_local + (size_t)idx * RQ + q;
-	const float4 v = *src;
-	if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
-	*src = make_float4(0.f, 0.f, 0.f, 0.f);  // self-cleaning accumulator
-	const int owner = idx / rows_per_rank;
-	float* dst = tab.sum[owner] + ((size_t)(idx - owner * rows_per_rank) * RQ + q) * 4;
-	red_add_v4(dst, v);
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const bool touched = idx < P && tiles_touched[idx] != 0;
+	unsigned m = __ballot_sync(0xffffffffu, touched);
+	while (m) {
+		const int rid = idx - lane + (__ffs(m) - 1);
+		m &= m - 1;
+		bool nz = false;
+		if (lane < RQ) {
+			float4* src = acc_local + (size_t)rid * RQ + lane;
+			const float4 v = *src;
+			nz = !(v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f);
+			if (nz) {
+				*src = make_float4(0.f, 0.f, 0.f, 0.f);
+				const int owner = rid / rows_per_rank;
+				red_add_v4(tab.sum[owner] + ((size_t)(rid - owner * rows_per_rank) * RQ + lane) * 4, v);
+			}
+		}
+		const unsigned any_nz = __ballot_sync(0xffffffffu, nz);
+		if (any_nz != 0 && lane == 0) {
+			const int owner = rid / rows_per_rank;
+			tab.mark[owner][rid - owner * rows_per_rank] = 1;   // idempotent byte store into the owner's window
+		}
+	}
 }
 
 // All-to-all barrier through flags in peer memory: thread p tells peer p "rank `rank` reached `epoch`", then waits until
@@ -107,34 +126,42 @@ __global__ void exchange_barrier_kernel(int rank, int world, uint32_t epoch, Pee
 	__threadfence_system();
 }
 
+// The owner's pass: one thread per owned row reads its mark (set by the pushers) and its dirty flag (row was non-zero in `full`
+// after the previous step); the rows found by a warp are copied, RQ lanes at a time, from `sum` to the `full` array of EVERY rank
+// (one multicast store, or world plain stores) and `sum` is cleared.  Rows that carried something last step and nothing now are
+// rewritten with zeros once.
 template <int RQ>
 __global__ void __launch_bounds__(256) exchange_spread_kernel(int P, int rows_per_rank, int rank, int world, float4* __restrict__ my_sum,
-                                                              uint8_t* __restrict__ dirty, const int* __restrict__ radii, PeerTable tab) {
-	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const int local = (int)(t / RQ), q = (int)(t % RQ);
-	const int idx = rank * rows_per_rank + local;
-	if (local >= rows_per_rank || idx >= P) return;
-	if (!(radii[idx] > 0)) return;  // never rendered: backward-preprocess does not read its row
-	float4* src = my_sum + (size_t)local * RQ + q;
-	const float4 v = *src;
-	const bool nz = !(v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f);
-	// a row is (re)written when any of its quarters is non-zero now or was non-zero after the previous step
-	// the RQ threads of a row are consecutive, RQ-aligned lanes, and leave together on the tests above
-	const unsigned group = ((1u << RQ) - 1u) << ((threadIdx.x & 31) & ~(RQ - 1));
-	const bool row_nz = __any_sync(group, nz);
-	const bool was = dirty[local] != 0;
-	__syncwarp(group);
-	if (nz) *src = make_float4(0.f, 0.f, 0.f, 0.f);
-	if (row_nz || was) {
-		if (tab.full_multicast != nullptr) {
-			// one 16-byte store on the multicast mapping: the NVSwitch replicates it into every rank's window (this rank's included)
-			asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(tab.full_multicast + ((size_t)idx * RQ + q) * 4), "f"(v.x),
-			             "f"(v.y), "f"(v.z), "f"(v.w)
-			             : "memory");
-		} else {
-			for (int p = 0; p < world; p++) reinterpret_cast<float4*>(tab.full[p])[(size_t)idx * RQ + q] = v;
+                                                              uint8_t* __restrict__ dirty, uint8_t* __restrict__ my_mark, PeerTable tab) {
+	const int local = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const bool valid = local < rows_per_rank && rank * rows_per_rank + local < P;
+	const bool work = valid && ((my_mark[local] | dirty[local]) != 0);
+	unsigned m = __ballot_sync(0xffffffffu, work);
+	while (m) {
+		const int l = local - lane + (__ffs(m) - 1);
+		m &= m - 1;
+		const size_t idx = (size_t)rank * rows_per_rank + l;
+		bool nz = false;
+		if (lane < RQ) {
+			float4* src = my_sum + (size_t)l * RQ + lane;
+			const float4 v = *src;
+			nz = !(v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f);
+			if (nz) *src = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (tab.full_multicast != nullptr) {
+				// one 16-byte store on the multicast mapping: the NVSwitch replicates it into every rank's window (this rank's included)
+				asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(tab.full_multicast + (idx * RQ + lane) * 4), "f"(v.x),
+				             "f"(v.y), "f"(v.z), "f"(v.w)
+				             : "memory");
+			} else {
+				for (int p = 0; p < world; p++) reinterpret_cast<float4*>(tab.full[p])[idx * RQ + lane] = v;
+			}
 		}
-		if (q == 0) dirty[local] = row_nz ? 1 : 0;
+		const unsigned row_nz = __ballot_sync(0xffffffffu, nz);
+		if (lane == 0) {
+			dirty[l] = row_nz != 0 ? 1 : 0;
+			my_mark[l] = 0;
+		}
 	}
 }
 
@@ -158,7 +185,8 @@ static void layout(rgs_exchange* ex) {
 	ex->rows_per_rank_cap = (ex->capacity + ex->world - 1) / ex->world;
 	ex->off_full = align_up((size_t)ex->rows_per_rank_cap * row, 256);
 	ex->off_flags = ex->off_full + align_up((size_t)ex->capacity * row, 256);
-	ex->bytes = ex->off_flags + 256;
+	ex->off_mark = ex->off_flags + 256;
+	ex->bytes = ex->off_mark + align_up((size_t)ex->rows_per_rank_cap, 256);
 }
 
 
@@ -222,6 +250,7 @@ int32_t rgs_exchange_attach(int32_t rank, int32_t world, int64_t capacity_rows, 
 		ex->tab.sum[p] = reinterpret_cast<float*>(ex->peer_base[p]);
 		ex->tab.full[p] = reinterpret_cast<float*>(ex->peer_base[p] + ex->off_full);
 		ex->tab.flags[p] = reinterpret_cast<uint32_t*>(ex->peer_base[p] + ex->off_flags);
+		ex->tab.mark[p] = reinterpret_cast<uint8_t*>(ex->peer_base[p] + ex->off_mark);
 	}
 	ex->base = ex->peer_base[rank];
 	ex->tab.full_multicast = multicast_ptr ? reinterpret_cast<float*>(reinterpret_cast<char*>(multicast_ptr) + ex->off_full) : nullptr;
@@ -249,6 +278,7 @@ int32_t rgs_exchange_connect(rgs_exchange* ex, const void* all_handles) {
 		ex->tab.sum[p] = reinterpret_cast<float*>(ex->peer_base[p]);
 		ex->tab.full[p] = reinterpret_cast<float*>(ex->peer_base[p] + ex->off_full);
 		ex->tab.flags[p] = reinterpret_cast<uint32_t*>(ex->peer_base[p] + ex->off_flags);
+		ex->tab.mark[p] = reinterpret_cast<uint8_t*>(ex->peer_base[p] + ex->off_mark);
 	}
 	ex->connected = true;
 	return RGS_OK;
@@ -296,21 +326,20 @@ int32_t rgs_exchange_rows(rgs_exchange* ex, int32_t P, const uint32_t* tiles_tou
 		// same sequence of P, so all do this in the same step; peers write into `full` only after the next barrier.
 		RGS_X_TRY(cudaMemsetAsync(ex->base + ex->off_full, 0, (size_t)ex->capacity * ex->row_floats * sizeof(float), s));
 		RGS_X_TRY(cudaMemsetAsync(ex->dirty, 0, (size_t)ex->rows_per_rank_cap, s));
-		ex->last_P = P;
+		ex->last_P = P;   // (marks and `sum` are always left clear by the spread pass)
 	}
 	{
-		const int64_t threads = (int64_t)P * rq;
-		const unsigned blocks = (unsigned)((threads + 255) / 256);
+		const unsigned blocks = (unsigned)((P + 255) / 256);
 		if (rq == 4) exchange_push_kernel<4><<<blocks, 256, 0, s>>>(P, rows_per_rank, reinterpret_cast<float4*>(ex->acc_local), tiles_touched, ex->tab);
 		else exchange_push_kernel<8><<<blocks, 256, 0, s>>>(P, rows_per_rank, reinterpret_cast<float4*>(ex->acc_local), tiles_touched, ex->tab);
 	}
 	exchange_barrier_kernel<<<1, 32, 0, s>>>(ex->rank, ex->world, ++ex->epoch, ex->tab, tf);
 	{
-		const int64_t threads = (int64_t)rows_per_rank * rq;
-		const unsigned blocks = (unsigned)((threads + 255) / 256);
+		const unsigned blocks = (unsigned)((rows_per_rank + 255) / 256);
 		float4* my_sum = reinterpret_cast<float4*>(ex->base);
-		if (rq == 4) exchange_spread_kernel<4><<<blocks, 256, 0, s>>>(P, rows_per_rank, ex->rank, ex->world, my_sum, ex->dirty, radii, ex->tab);
-		else exchange_spread_kernel<8><<<blocks, 256, 0, s>>>(P, rows_per_rank, ex->rank, ex->world, my_sum, ex->dirty, radii, ex->tab);
+		uint8_t* my_mark = reinterpret_cast<uint8_t*>(ex->base + ex->off_mark);
+		if (rq == 4) exchange_spread_kernel<4><<<blocks, 256, 0, s>>>(P, rows_per_rank, ex->rank, ex->world, my_sum, ex->dirty, my_mark, ex->tab);
+		else exchange_spread_kernel<8><<<blocks, 256, 0, s>>>(P, rows_per_rank, ex->rank, ex->world, my_sum, ex->dirty, my_mark, ex->tab);
 	}
 	exchange_barrier_kernel<<<1, 32, 0, s>>>(ex->rank, ex->world, ++ex->epoch, ex->tab, tf);
 	count_launch(4);

@@ -64,6 +64,18 @@ def _worker(rank, world, port, outdir, exchange_mode, variant, compact=False):
             for k in a:
                 x, y = a[k].float(), b[k].float()
                 res[f"{step}/{k}"] = (float((x - y).abs().max()), float(y.abs().max()), float((x - y).norm() / (y.norm() + 1e-30)))
+                if k in ("color", "depth", "normal", "coord", "alpha") and not torch.equal(a[k], b[k]):
+                    # evidence for an intermittent few-pixel difference: where, which rank's slab, and which of the two renders repeats
+                    bad = torch.nonzero((a[k] != b[k]).any(0))[:4].tolist()
+                    rows = [(min(s0 * 16, sc.height), min(s1 * 16, sc.height)) for s0, s1 in sharded.slabs]
+                    with torch.no_grad():
+                        again_single = single(sc.means3D[:n], torch.zeros_like(sc.means3D[:n]), sc.opacities[:n], shs=sc.shs[:n], scales=sc.scales[:n],
+                                              rotations=sc.rotations[:n])
+                    idx = {"color": 0, "coord": 2, "depth": 4, "alpha": 6, "normal": 7}[k]
+                    res[f"{step}/{k}/evidence"] = {
+                        "pixels(y,x)": bad, "slab_owner": [next(r for r, (r0, r1) in enumerate(rows) if r0 <= y < r1) for y, x in bad],
+                        "gathered": [a[k][:, y, x].tolist() for y, x in bad], "single": [b[k][:, y, x].tolist() for y, x in bad],
+                        "single_again": [again_single[idx][:, y, x].tolist() for y, x in bad]}
             # are the replicated gradients the same bits on every rank?
             flat = torch.cat([a[k].reshape(-1).float() for k in sorted(a) if k.startswith("g_")])
             ref = flat.clone()
@@ -93,11 +105,13 @@ def test_sharded_equals_single(world, exchange, variant, compact, tmp_path):
     for rank in range(world):
         res = np.load(tmp_path / f"res{rank}.npy", allow_pickle=True).item()
         for key, val in res.items():
-            step, k = key.split("/")
+            step, k = key.split("/")[:2]
             if k == "bits_differ_from_rank0":
                 assert val == 0, (rank, key, val)                 # replicated gradients: same bits everywhere
+            elif key.endswith("/evidence"):
+                continue
             elif k in ("color", "depth", "normal", "coord", "alpha", "radii"):
-                assert val[0] == 0.0, (rank, key, val)            # slabs reproduce the single-GPU image bit for bit
+                assert val[0] == 0.0, (rank, key, val, res.get(key + "/evidence"))   # slabs reproduce the single-GPU image bit for bit
             else:
                 mx, ref, rel = val
                 assert rel < 1e-3 and mx <= 1e-2 * ref + 1e-6, (rank, key, val)
