@@ -385,26 +385,41 @@ __global__ void __launch_bounds__(128, 4) preprocess_backward_rows_kernel(FwdPar
 		preprocess_backward_row(p, g, radii, grad_accum, out, fix_mip, (int)list[l]);
 }
 
-// rows that need work: rendered and any non-zero (or NaN) entry in the accumulator row.  One warp-aggregated atomic per warp.
-__global__ void __launch_bounds__(256) nonzero_rows_kernel(int P, const int* __restrict__ radii, const float* __restrict__ grad_accum, int GF,
+// rows that need work: rendered and any non-zero (or NaN) entry in the accumulator row.  A warp owns 32 consecutive rows and reads them
+// as one contiguous block (lane-major float4, RQ passes of 512 bytes), folds the quarters of a row with a ballot, and appends the
+// surviving rows with ONE atomic per warp.
+template <int RQ>
+__global__ void __launch_bounds__(256) nonzero_rows_kernel(int P, const int* __restrict__ radii, const float4* __restrict__ grad_accum,
                                                             uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
-	bool nz = false;
-	if (idx < P && radii[idx] > 0) {
-		const float4* r = reinterpret_cast<const float4*>(grad_accum + (size_t)idx * GF);
-		for (int q = 0; q < GF / 4; q++) {
-			const float4 v = r[q];
-			nz = nz || !(v.x == 0.f) || !(v.y == 0.f) || !(v.z == 0.f) || !(v.w == 0.f);
-		}
+	const int row0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane;  // first of this warp's 32 rows
+	if (row0 >= P) return;
+	const int idx = row0 + lane;
+	const bool vis = idx < P && radii[idx] > 0;
+	const size_t n4 = (size_t)P * RQ;
+	unsigned rows_nz = 0;  // bit r: row row0 + r has a non-zero entry
+#pragma unroll
+	for (int k = 0; k < RQ; k++) {
+		const size_t e = (size_t)row0 * RQ + (size_t)k * 32 + lane;  // float4 index: row (k*32+lane)/RQ, quarter (k*32+lane)%RQ
+		float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (e < n4) v = grad_accum[e];
+		const bool nzq = !(v.x == 0.f) || !(v.y == 0.f) || !(v.z == 0.f) || !(v.w == 0.f);
+		unsigned b = __ballot_sync(0xffffffffu, nzq);  // bit j: float4 k*32+j
+		// fold groups of RQ bits into one bit per row
+#pragma unroll
+		for (int sft = 1; sft < RQ; sft <<= 1) b |= b >> sft;
+		// rows covered by this pass: (k*32)/RQ ... ; pick bit (r*RQ) of b for the r-th of them
+		constexpr int rows_per_pass = 32 / RQ;
+#pragma unroll
+		for (int r = 0; r < rows_per_pass; r++)
+			if ((b >> (r * RQ)) & 1u) rows_nz |= 1u << (k * rows_per_pass + r);
 	}
-	const unsigned m = __ballot_sync(0xffffffffu, nz);
-	if (m == 0) return;
-	const int leader = __ffs(m) - 1;
+	const unsigned keep = rows_nz & __ballot_sync(0xffffffffu, vis);
+	if (keep == 0) return;
 	uint32_t base = 0;
-	if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, leader);
-	if (nz) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)idx;
+	if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(keep));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if ((keep >> lane) & 1u) list[base + __popc(keep & ((1u << lane) - 1u))] = (uint32_t)idx;
 }
 
 // ---- SH backward (backward.cu:21-140): warp-cooperative so the [M,3] rows move through shared memory coalesced ------
@@ -560,8 +575,9 @@ __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_kernel(int P, int D
 	if (split) sh_block_copy<false>(tile, stride, 3, row - 3, count, nullptr, d_sh_rest + (size_t)g0 * (row - 3), lane);
 }
 
-// compacted form of the SH backward: a warp takes 32 LISTED Gaussians, gathers their coefficient rows (12*M contiguous bytes each)
-// into shared memory, lane = row as above, and scatters the dL_dsh rows back; all other rows of dL_dsh were zero-filled.
+// compacted form of the SH backward: lane = one LISTED Gaussian.  The rows are scattered in memory anyway, so every lane fetches its own
+// coefficient row (12*M contiguous bytes: twelve independent 128-bit loads in flight when the layout allows) into its shared-memory
+// scratch row, works on it in place as above and stores dL_dsh back the same way; all other rows of dL_dsh were zero-filled.
 __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_rows_kernel(int D, int M, const float* __restrict__ means3D, const float* __restrict__ cam_pos,
                                                                           const float* __restrict__ shs, const float* __restrict__ shs_rest,
                                                                           const uint8_t* __restrict__ clamped, const float* __restrict__ grad_accum, int GF,
@@ -571,48 +587,49 @@ __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_rows_kernel(int D, 
 	extern __shared__ float s_sh[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int row = 3 * M, stride = row | 1;
-	float* tile = s_sh + (size_t)warp * 32 * stride;
+	float* sh = s_sh + ((size_t)warp * 32 + lane) * stride;
 	const bool split = shs_rest != nullptr;
+	const bool vec = !split && (row & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_sh) & 15) == 0;
 	const int n = (int)*count;
-	for (int l0 = (blockIdx.x * SH_WARPS + warp) * 32; l0 < n; l0 += gridDim.x * SH_WARPS * 32) {
-		const int mine = (l0 + lane < n) ? (int)list[l0 + lane] : -1;
-		bool need = false;  // a zero colour gradient (after the clamp mask) leaves dL_dsh = 0 and no view-direction term
-		if (mine >= 0) {
-			const uint8_t cb = clamped[mine];
-			const float* ga = grad_accum + (size_t)mine * GF + G_COL;
-			need = (!(cb & 1) && !(ga[0] == 0.f)) || (!(cb & 2) && !(ga[1] == 0.f)) || (!(cb & 4) && !(ga[2] == 0.f));
+	for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
+		const int rid = (int)list[l];
+		const uint8_t cb = clamped[rid];
+		const float* ga = grad_accum + (size_t)rid * GF + G_COL;
+		// a zero colour gradient (after the clamp mask) leaves dL_dsh = 0 and no view-direction term: nothing to read or write
+		if (!((!(cb & 1) && !(ga[0] == 0.f)) || (!(cb & 2) && !(ga[1] == 0.f)) || (!(cb & 4) && !(ga[2] == 0.f)))) continue;
+		if (vec) {
+			const float4* src = reinterpret_cast<const float4*>(shs + (size_t)rid * row);
+			float4 v[12];
+#pragma unroll
+			for (int q = 0; q < 12; q++)
+				if (4 * q < row) v[q] = __ldg(src + q);
+#pragma unroll
+			for (int q = 0; q < 12; q++)
+				if (4 * q < row) { sh[4 * q] = v[q].x; sh[4 * q + 1] = v[q].y; sh[4 * q + 2] = v[q].z; sh[4 * q + 3] = v[q].w; }
+		} else if (!split) {
+			const float* src = shs + (size_t)rid * row;
+			for (int e = 0; e < row; e++) sh[e] = __ldg(src + e);
+		} else {
+			const float* s0 = shs + (size_t)rid * 3;
+			const float* s1 = shs_rest + (size_t)rid * (row - 3);
+			sh[0] = __ldg(s0); sh[1] = __ldg(s0 + 1); sh[2] = __ldg(s0 + 2);
+			for (int e = 0; e < row - 3; e++) sh[3 + e] = __ldg(s1 + e);
 		}
-		const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-		for (unsigned m = need_mask; m; m &= m - 1) {
-			const int r = __ffs(m) - 1;
-			const int rid = __shfl_sync(0xffffffffu, mine, r);
-			float* dst = tile + r * stride;
-			if (!split) {
-				const float* src = shs + (size_t)rid * row;
-				for (int e = lane; e < row; e += 32) dst[e] = __ldg(src + e);
-			} else {
-				if (lane < 3) dst[lane] = __ldg(shs + (size_t)rid * 3 + lane);
-				const float* src = shs_rest + (size_t)rid * (row - 3);
-				for (int e = lane; e < row - 3; e += 32) dst[3 + e] = __ldg(src + e);
-			}
+		sh_backward_row(sh, rid, D, M, means3D, cam_pos, clamped, grad_accum, GF, d_means3D);
+		if (vec) {
+			float4* dst = reinterpret_cast<float4*>(d_sh + (size_t)rid * row);
+#pragma unroll
+			for (int q = 0; q < 12; q++)
+				if (4 * q < row) dst[q] = make_float4(sh[4 * q], sh[4 * q + 1], sh[4 * q + 2], sh[4 * q + 3]);
+		} else if (!split) {
+			float* dst = d_sh + (size_t)rid * row;
+			for (int e = 0; e < row; e++) dst[e] = sh[e];
+		} else {
+			float* d0 = d_sh + (size_t)rid * 3;
+			float* d1 = d_sh_rest + (size_t)rid * (row - 3);
+			d0[0] = sh[0]; d0[1] = sh[1]; d0[2] = sh[2];
+			for (int e = 0; e < row - 3; e++) d1[e] = sh[3 + e];
 		}
-		__syncwarp();
-		if (need) sh_backward_row(tile + lane * stride, mine, D, M, means3D, cam_pos, clamped, grad_accum, GF, d_means3D);
-		__syncwarp();
-		for (unsigned m = need_mask; m; m &= m - 1) {
-			const int r = __ffs(m) - 1;
-			const int rid = __shfl_sync(0xffffffffu, mine, r);
-			const float* src = tile + r * stride;
-			if (!split) {
-				float* dst = d_sh + (size_t)rid * row;
-				for (int e = lane; e < row; e += 32) dst[e] = src[e];
-			} else {
-				if (lane < 3) d_sh[(size_t)rid * 3 + lane] = src[lane];
-				float* dst = d_sh_rest + (size_t)rid * (row - 3);
-				for (int e = lane; e < row - 3; e += 32) dst[e] = src[3 + e];
-			}
-		}
-		__syncwarp();
 	}
 }
 
@@ -657,13 +674,19 @@ void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii
 	uint32_t* count = reinterpret_cast<uint32_t*>(g.scan_temp);
 	cudaMemsetAsync(count, 0, sizeof(uint32_t), s);
 	const int GF = grad_floats(p.coord);
-	nonzero_rows_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p.P, radii, grad_accum, GF, list, count);
+	if (GF == GRAD_FLOATS_BASE)
+		nonzero_rows_kernel<GRAD_FLOATS_BASE / 4><<<(p.P + 255) / 256, 256, 0, s>>>(p.P, radii, reinterpret_cast<const float4*>(grad_accum), list, count);
+	else
+		nonzero_rows_kernel<GRAD_FLOATS_COORD / 4><<<(p.P + 255) / 256, 256, 0, s>>>(p.P, radii, reinterpret_cast<const float4*>(grad_accum), list, count);
+	// the list length stays on the device (no host sync): grids sized for "every row listed", CTAs beyond the list leave at once
 	const int sms = 148;
-	preprocess_backward_rows_kernel<<<sms * 4, 128, 0, s>>>(p, g, radii, grad_accum, out, fix_mip, list, count);
+	const int rows_grid = min((p.P + 127) / 128, sms * 16);
+	preprocess_backward_rows_kernel<<<rows_grid, 128, 0, s>>>(p, g, radii, grad_accum, out, fix_mip, list, count);
 	count_launch(2 + 8 + (has_sh ? 1 : 0));
 	if (has_sh) {
 		if (smem > 48 * 1024) ensure_dynamic_smem(sh_backward_rows_kernel, smem, configured_rows);
-		sh_backward_rows_kernel<<<sms * 2, SH_WARPS * 32, smem, s>>>(p.D, p.M, p.means3D, p.cam_pos, p.shs, p.shs_rest, g.clamped, grad_accum, GF, out.d_sh,
+		const int sh_grid = min((p.P + SH_WARPS * 32 - 1) / (SH_WARPS * 32), sms * 8);
+		sh_backward_rows_kernel<<<sh_grid, SH_WARPS * 32, smem, s>>>(p.D, p.M, p.means3D, p.cam_pos, p.shs, p.shs_rest, g.clamped, grad_accum, GF, out.d_sh,
 		                                                            out.d_sh_rest, out.d_means3D, list, count);
 		count_launch();
 	}
