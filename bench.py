@@ -347,13 +347,14 @@ def main():
         # Host inputs of one training step, as train.py has them: the camera (matrices, position, background) and the
         # ground-truth photograph, 8 bits per channel like every dataset the reference reads (PNG/JPEG).  Depth / normal
         # supervision in RaDe-GS is self-consistency between rendered maps, so no ground truth is shipped for them.
+        r0, r1 = min(slab[0] * 16, H), min(slab[1] * 16, H)
+        # multi-GPU: a rank's loss needs the ground-truth rows of its own slab only, so that is what it copies in
         host = {"view": sc_cpu.viewmatrix.pin_memory(), "proj": sc_cpu.projmatrix.pin_memory(), "campos": sc_cpu.campos.pin_memory(),
-                "bg": sc_cpu.bg.pin_memory(), "gt_color": (torch.rand(3, H, W) * 255).to(torch.uint8).pin_memory()}
+                "bg": sc_cpu.bg.pin_memory(), "gt_color": (torch.rand(3, H, W) * 255).to(torch.uint8)[:, r0:r1].contiguous().pin_memory()}
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
         leaves = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
         copy_stream = torch.cuda.Stream(device=dev)
-        r0, r1 = min(slab[0] * 16, H), min(slab[1] * 16, H)
 
         def step_e2e():
             for k in ("view", "proj", "campos", "bg"):                 # camera: needed by forward, current stream
@@ -377,7 +378,7 @@ def main():
                                                                                      leaves["opacities"], leaves["scales"], leaves["rotations"])
             torch.cuda.current_stream().wait_stream(copy_stream)
             sl = slice(0, r1 - r0) if multi else slice(r0, r1)   # compact maps start at the slab's first row
-            gsl = slice(r0, r1)
+            gsl = slice(0, r1 - r0)                                 # the ground truth held on the device is this rank's rows
             # photometric L1 against the 8-bit ground truth + small regularisers that keep the depth / normal / alpha gradient
             # paths live (stand-ins for train.py's depth-normal consistency terms, which also need no ground truth)
             loss = (color[:, sl] - dbuf["gt_color"][:, gsl].float() * (1.0 / 255.0)).abs().mean() + 0.01 * alpha[:, sl].mean()
