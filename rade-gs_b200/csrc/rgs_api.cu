@@ -405,8 +405,8 @@ int32_t rgs_backward_render_exchange(const rgs_camera* cam, const rgs_gaussians*
 	return debug_sync(cam, s, "gradient exchange");
 }
 
-int32_t rgs_backward_preprocess(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, const float* grad_accum,
-                                const rgs_backward_out* out, void* cuda_stream) {
+static int32_t backward_preprocess_impl(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, const float* grad_accum,
+                                        const rgs_backward_out* out, void* cuda_stream, bool prefilled) {
 	FwdParams p;
 	GeomView g;
 	BinView b;
@@ -419,8 +419,31 @@ int32_t rgs_backward_preprocess(const rgs_camera* cam, const rgs_gaussians* gs, 
 	ParamGradOut po{out->dL_dmeans2D, out->dL_dcolors, out->dL_dopacity, out->dL_dmeans3D, out->dL_dcov3D, out->dL_dsh, out->dL_dscales, out->dL_drotations, out->dL_dsh_rest};
 	if ((p.shs_rest != nullptr) != (po.d_sh_rest != nullptr) && po.d_sh != nullptr)
 		return fail(RGS_E_INVALID, "dL_dsh_rest must be given exactly when shs_rest is");
-	{ StageScope sc(ST_PREPROCESS_BWD, s); launch_preprocess_backward(p, g, in->radii, grad_accum, po, s); }
+	{ StageScope sc(ST_PREPROCESS_BWD, s); launch_preprocess_backward(p, g, in->radii, grad_accum, po, s, prefilled); }
 	return debug_sync(cam, s, "backward preprocess");
+}
+
+int32_t rgs_backward_preprocess(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, const float* grad_accum,
+                                const rgs_backward_out* out, void* cuda_stream) {
+	return backward_preprocess_impl(cam, gs, in, grad_accum, out, cuda_stream, false);
+}
+
+// per-device side stream + events for work that may run underneath the main stream's kernels
+struct SideStream {
+	cudaStream_t stream = nullptr;
+	cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+	static thread_local SideStream per_dev[64];
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+	SideStream& ss = per_dev[dev & 63];
+	if (!ss.stream) {
+		if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+		if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess)
+			return nullptr;
+	}
+	return &ss;
 }
 
 int32_t rgs_backward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_backward_in* in, const rgs_backward_out* out,
@@ -428,12 +451,29 @@ int32_t rgs_backward(const rgs_camera* cam, const rgs_gaussians* gs, const rgs_b
 	if (!gs || !cam) return fail(RGS_E_INVALID, "null camera / gaussians");
 	if (gs->P == 0) return RGS_OK;
 	if (!grad_scratch) return fail(RGS_E_INVALID, "null scratch callback");
+	if (!out) return fail(RGS_E_INVALID, "null gradient accumulator / outputs");
 	const size_t bytes = (size_t)gs->P * grad_floats(cam->require_coord != 0) * sizeof(float);
 	float* acc = reinterpret_cast<float*>(grad_scratch(grad_scratch_user, bytes));
 	if (!acc) return fail(RGS_E_ALLOC, "gradient scratch callback returned NULL");
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	// The zero-fill of the dense gradient tensors (pure HBM writes, ~280 MB at 1 M Gaussians) runs on a side stream underneath the
+	// issue-bound backward blend; everything queued on `s` before this call is ordered before it (the tensors may be recycled memory).
+	bool prefilled = false;
+	SideStream* ss = (backward_preprocess_is_compacted() && !cam->debug) ? side_stream() : nullptr;
+	if (ss) {
+		FwdParams p;
+		int rc0 = make_params(cam, gs, p);
+		if (rc0 != RGS_OK) return rc0;
+		ParamGradOut po{out->dL_dmeans2D, out->dL_dcolors, out->dL_dopacity, out->dL_dmeans3D, out->dL_dcov3D, out->dL_dsh, out->dL_dscales, out->dL_drotations, out->dL_dsh_rest};
+		if (cudaEventRecord(ss->fork, s) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
+			launch_backward_zero_fill(p, po, ss->stream);
+			prefilled = cudaEventRecord(ss->join, ss->stream) == cudaSuccess;
+		}
+	}
 	int rc = rgs_backward_render(cam, gs, in, acc, cuda_stream);
+	if (prefilled && cudaStreamWaitEvent(s, ss->join, 0) != cudaSuccess) return fail(RGS_E_CUDA, "cudaStreamWaitEvent failed");
 	if (rc != RGS_OK) return rc;
-	return rgs_backward_preprocess(cam, gs, in, acc, out, cuda_stream);
+	return backward_preprocess_impl(cam, gs, in, acc, out, cuda_stream, prefilled);
 }
 
 int32_t rgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* /*projmatrix*/, uint8_t* present, void* cuda_stream) {

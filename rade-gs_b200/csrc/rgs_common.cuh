@@ -238,7 +238,11 @@ void launch_render_backward(const FwdParams& p, GeomView g, BinView b, ImgView i
 struct ParamGradOut {
 	float *d_means2D, *d_colors, *d_opacity, *d_means3D, *d_cov3D, *d_sh, *d_scales, *d_rotations, *d_sh_rest;
 };
-void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s);
+// prefilled: the outputs were already zero-filled by launch_backward_zero_fill (possibly on another stream, joined by the caller)
+void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s,
+                                bool prefilled = false);
+void launch_backward_zero_fill(const FwdParams& p, ParamGradOut out, cudaStream_t s);
+bool backward_preprocess_is_compacted();
 
 // fused activations / densification statistics (rgs_activation.cu)
 void launch_activate_forward(int P, const float* raw_scaling, const float* raw_opacity, const float* raw_rotation, const float* filter_3D, float* scales,

@@ -633,9 +633,34 @@ __global__ void __launch_bounds__(SH_WARPS * 32) sh_backward_rows_kernel(int D, 
 	}
 }
 
-void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s) {
-	static const int fix_mip = getenv("RGS_FIX_MIP_GRADIENT") != nullptr && atoi(getenv("RGS_FIX_MIP_GRADIENT")) != 0;
+bool backward_preprocess_is_compacted() {
 	static const bool dense = getenv("RGS_BWD_PREPROCESS") != nullptr && std::string(getenv("RGS_BWD_PREPROCESS")) == "dense";
+	return !dense;
+}
+
+// zero-fill of the nine dense gradient tensors (what the compacted kernels do not write).  Pure HBM writes: rgs_backward issues it on
+// a side stream so that it runs underneath the issue-bound backward blend.
+void launch_backward_zero_fill(const FwdParams& p, ParamGradOut out, cudaStream_t s) {
+	const size_t P = (size_t)p.P;
+	const bool has_sh = p.shs != nullptr && out.d_sh != nullptr && p.M > 0;
+	const bool split = p.shs_rest != nullptr;
+	cudaMemsetAsync(out.d_means2D, 0, P * 3 * sizeof(float), s);
+	cudaMemsetAsync(out.d_colors, 0, P * 3 * sizeof(float), s);
+	cudaMemsetAsync(out.d_opacity, 0, P * sizeof(float), s);
+	cudaMemsetAsync(out.d_means3D, 0, P * 3 * sizeof(float), s);
+	cudaMemsetAsync(out.d_cov3D, 0, P * 6 * sizeof(float), s);
+	cudaMemsetAsync(out.d_scales, 0, P * 3 * sizeof(float), s);
+	cudaMemsetAsync(out.d_rotations, 0, P * 4 * sizeof(float), s);
+	if (has_sh) {
+		cudaMemsetAsync(out.d_sh, 0, P * (split ? 3 : 3 * p.M) * sizeof(float), s);
+		if (split && out.d_sh_rest != nullptr) cudaMemsetAsync(out.d_sh_rest, 0, P * (3 * p.M - 3) * sizeof(float), s);
+	}
+}
+
+void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii, const float* grad_accum, ParamGradOut out, cudaStream_t s,
+                                bool prefilled) {
+	static const int fix_mip = getenv("RGS_FIX_MIP_GRADIENT") != nullptr && atoi(getenv("RGS_FIX_MIP_GRADIENT")) != 0;
+	const bool dense = !backward_preprocess_is_compacted();
 	const bool has_sh = p.shs != nullptr && out.d_sh != nullptr && p.M > 0;
 	const int stride = (3 * p.M) | 1;
 	const size_t smem = (size_t)SH_WARPS * 32 * stride * sizeof(float);
@@ -657,19 +682,7 @@ void launch_preprocess_backward(const FwdParams& p, GeomView g, const int* radii
 	// compacted: zero-fill the outputs (memsets run at HBM write speed), list the rows that received anything, run the chains on those.
 	// The list lives in the geometry buffer's `offsets` array (only the cross-check radix path of forward uses it), its length in the
 	// first word of the scan scratch.
-	const size_t P = (size_t)p.P;
-	const bool split = p.shs_rest != nullptr;
-	cudaMemsetAsync(out.d_means2D, 0, P * 3 * sizeof(float), s);
-	cudaMemsetAsync(out.d_colors, 0, P * 3 * sizeof(float), s);
-	cudaMemsetAsync(out.d_opacity, 0, P * sizeof(float), s);
-	cudaMemsetAsync(out.d_means3D, 0, P * 3 * sizeof(float), s);
-	cudaMemsetAsync(out.d_cov3D, 0, P * 6 * sizeof(float), s);
-	cudaMemsetAsync(out.d_scales, 0, P * 3 * sizeof(float), s);
-	cudaMemsetAsync(out.d_rotations, 0, P * 4 * sizeof(float), s);
-	if (has_sh) {
-		cudaMemsetAsync(out.d_sh, 0, P * (split ? 3 : 3 * p.M) * sizeof(float), s);
-		if (split && out.d_sh_rest != nullptr) cudaMemsetAsync(out.d_sh_rest, 0, P * (3 * p.M - 3) * sizeof(float), s);
-	}
+	if (!prefilled) launch_backward_zero_fill(p, out, s);
 	uint32_t* list = g.offsets;
 	uint32_t* count = reinterpret_cast<uint32_t*>(g.scan_temp);
 	cudaMemsetAsync(count, 0, sizeof(uint32_t), s);
