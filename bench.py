@@ -277,6 +277,8 @@ def main():
         from rade_gs_b200 import multigpu
     sc_cpu, coord, depth = scenes.make_config(a.config)
     sc = sc_cpu.to(dev)
+    if multi:
+        sc = multigpu.broadcast_scene_(sc)   # replicated model state: rank 0's bits everywhere
     W, H, P = sc.width, sc.height, sc.means3D.shape[0]
     grads = scenes.make_upstream_grads(H, W, device=dev)
     grid_y = (H + 15) // 16

@@ -115,6 +115,22 @@ def exchange_sum_(acc: torch.Tensor, group=None, mode: str | None = None) -> tor
     return acc
 
 
+def broadcast_scene_(scene, src: int = 0, group=None):
+    """Make a replicated scene (any object whose tensor attributes are the model / camera state) bit-identical on every rank by
+    broadcasting rank `src`'s copy -- what a trainer does with its replicated parameters.  Data-parallel slabs only compose to the
+    single-GPU image if every rank rasterizes THE SAME numbers: two processes that each synthesise "the same" scene on their CPUs can
+    differ in the last bits (threaded vectorised exp / sigmoid / matmul tails), and a few-ulp difference in one splat is a visible
+    few-pixel difference in the gathered image."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return scene
+    for k, v in list(vars(scene).items()):
+        if isinstance(v, torch.Tensor):
+            t = v.contiguous()
+            dist.broadcast(t, src=src, group=group)
+            setattr(scene, k, t)
+    return scene
+
+
 class GradExchange:
     """The one exchange step of the sharded backward: slab-local accumulator rows -> summed rows on every rank.
 

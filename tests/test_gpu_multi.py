@@ -20,7 +20,7 @@ def _worker(rank, world, port, outdir, exchange_mode, variant, compact=False):
     import torch.distributed as dist
     import diff_gaussian_rasterization as dgr
     from rade_gs_b200 import scenes
-    from rade_gs_b200.multigpu import GradExchange, ShardedGaussianRasterizer
+    from rade_gs_b200.multigpu import GradExchange, ShardedGaussianRasterizer, broadcast_scene_
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -30,6 +30,7 @@ def _worker(rank, world, port, outdir, exchange_mode, variant, compact=False):
     try:
         coord, depth, ks = variant
         sc = scenes.make_scene(60000, 640, 400, 500.0, -3.8, seed=21, view=scenes.look_at_view((0.3, 0.2, -0.4), (0.0, 0.1, 6.0)), bg=(0.2, 0.1, 0.3)).to(dev)
+        sc = broadcast_scene_(sc)   # replicated state = rank 0's bits on every rank, as in a trainer
         st = dgr.GaussianRasterizationSettings(sc.height, sc.width, sc.tanfovx, sc.tanfovy, ks, sc.bg, 1.0, sc.viewmatrix, sc.projmatrix, 3, sc.campos,
                                                False, depth, coord, False)
         P = sc.means3D.shape[0]
@@ -82,6 +83,14 @@ def _worker(rank, world, port, outdir, exchange_mode, variant, compact=False):
             dist.broadcast(ref, src=0)
             res[f"{step}/bits_differ_from_rank0"] = int((flat.view(torch.int32) != ref.view(torch.int32)).sum())
         np.save(os.path.join(outdir, f"res{rank}.npy"), res, allow_pickle=True)
+        ev = {k: v for k, v in res.items() if k.endswith("/evidence")}
+        if ev:   # keep the full evidence where the driver of the GPU box can collect it
+            try:
+                os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+                with open(os.path.join(ROOT, "gpurun_out", "multi_mismatch_evidence.txt"), "a") as f:
+                    f.write(f"world {world} rank {rank} exchange {exchange_mode} variant {variant} compact {compact}: {ev}\n")
+            except OSError:
+                pass
     finally:
         if ex is not None:
             ex.close()
