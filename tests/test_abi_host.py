@@ -48,6 +48,53 @@ def test_argument_validation_without_gpu():
     assert lib.rgs_forward(None, None, None, None, None) == -1
 
 
+def test_host_side_rejections_through_the_struct_abi():
+    """make_params runs before any CUDA call: more than 16 SH coefficients (the SH kernels stage rows of <= 16 x 3 floats), a slab
+    outside the tile grid, prefiltered=True and the exchange's argument checks come back as statuses with messages."""
+    lib = ctypes.CDLL(LIB)
+    lib.rgs_last_error.restype = ctypes.c_char_p
+    lib.rgs_forward.restype = ctypes.c_int64
+
+    class Cam(ctypes.Structure):
+        _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32), ("tan_fovx", ctypes.c_float), ("tan_fovy", ctypes.c_float),
+                    ("kernel_size", ctypes.c_float), ("scale_modifier", ctypes.c_float), ("viewmatrix", ctypes.c_void_p), ("projmatrix", ctypes.c_void_p),
+                    ("cam_pos", ctypes.c_void_p), ("background", ctypes.c_void_p), ("sh_degree", ctypes.c_int32), ("sh_coeffs", ctypes.c_int32),
+                    ("require_coord", ctypes.c_int32), ("require_depth", ctypes.c_int32), ("prefiltered", ctypes.c_int32), ("debug", ctypes.c_int32),
+                    ("tile_row_begin", ctypes.c_int32), ("tile_row_end", ctypes.c_int32), ("compact_slab", ctypes.c_int32)]
+
+    class Gs(ctypes.Structure):
+        _fields_ = [("P", ctypes.c_int32)] + [(n, ctypes.c_void_p) for n in ("means3D", "opacities", "shs", "colors_precomp", "scales", "rotations",
+                                                                             "cov3D_precomp", "shs_rest")]
+
+    fake = ctypes.c_void_p(0x1000)   # never dereferenced: every case below is rejected before the first CUDA call
+    out = (ctypes.c_void_p * 8)(*[fake] * 8)
+    bufs = (ctypes.c_void_p * 6)(*[fake] * 6)
+
+    def call(**kw):
+        cam = Cam(width=64, height=64, tan_fovx=0.5, tan_fovy=0.5, scale_modifier=1.0, sh_degree=3, sh_coeffs=16, tile_row_begin=0, tile_row_end=-1)
+        for k, v in kw.items():
+            setattr(cam, k, v)
+        gs = Gs(P=4, means3D=fake, opacities=fake, shs=fake, scales=fake, rotations=fake)
+        return lib.rgs_forward(ctypes.byref(cam), ctypes.byref(gs), out, bufs, None), lib.rgs_last_error()
+
+    rc, msg = call(sh_coeffs=20)
+    assert rc == -1 and b"at most 16 SH coefficients" in msg
+    rc, msg = call(sh_degree=3, sh_coeffs=9)
+    assert rc == -1 and b"sh_degree" in msg
+    rc, msg = call(tile_row_begin=3, tile_row_end=99)
+    assert rc == -1 and b"slab" in msg
+    rc, msg = call(prefiltered=1)
+    assert rc == -3 and b"prefiltered" in msg
+    lib.rgs_exchange_last_error.restype = ctypes.c_char_p
+    ex = ctypes.c_void_p()
+    handle = (ctypes.c_char * 64)()
+    assert lib.rgs_exchange_create(ctypes.c_int32(3), ctypes.c_int32(2), ctypes.c_int64(10), ctypes.c_int32(16), ctypes.byref(ex), handle) == -1
+    assert b"rank / world" in lib.rgs_exchange_last_error()
+    assert lib.rgs_exchange_create(ctypes.c_int32(0), ctypes.c_int32(2), ctypes.c_int64(10), ctypes.c_int32(17), ctypes.byref(ex), handle) == -1
+    lib.rgs_exchange_window_bytes.restype = ctypes.c_size_t
+    assert lib.rgs_exchange_window_bytes(ctypes.c_int32(8), ctypes.c_int64(1_000_000), ctypes.c_int32(16)) > 64_000_000 + 8_000_000
+
+
 def test_python_surface_matches_reference():
     import diff_gaussian_rasterization as dgr
     fields = ("image_height", "image_width", "tanfovx", "tanfovy", "kernel_size", "bg", "scale_modifier", "viewmatrix", "projmatrix",

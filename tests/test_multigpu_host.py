@@ -233,3 +233,30 @@ def test_slab_local_ssim_with_halo_rows_equals_the_whole_image_loss(tmp_path):
         assert not out.any()                                 # a rank's gradient lives in its own rows only
         grad[:, r0:r1] = r["grad"][:, r0:r1]
     assert torch.allclose(grad, x.grad, rtol=1e-9, atol=1e-12)  # including the rows next to slab boundaries (halo contributions)
+
+
+def _bcast_worker(rank, world, port, tmpdir):
+    sys.path.insert(0, os.path.join(ROOT, "rade-gs_b200"))
+    from types import SimpleNamespace
+    from rade_gs_b200 import multigpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(11)
+        sc = SimpleNamespace(means3D=torch.randn(100, 3, generator=g), scales=torch.rand(100, 3, generator=g), width=64, name="x")
+        if rank == 1:
+            sc.scales = sc.scales + 1e-7        # "the same scene", one ulp off on another rank
+            sc.means3D = sc.means3D.t().contiguous().t()   # and a non-contiguous view
+        multigpu.broadcast_scene_(sc)
+        torch.save({"means3D": sc.means3D.clone(), "scales": sc.scales.clone(), "width": sc.width}, os.path.join(tmpdir, f"bcast{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_scene_makes_the_replicated_state_bit_identical(tmp_path):
+    """Slabs only compose to the single-GPU image when every rank rasterizes the same bits (profiles/r02_crossrank_inputs_probe.txt)."""
+    port = 36500 + (os.getpid() % 2000)
+    mp.spawn(_bcast_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(tmp_path / f"bcast{r}.pt") for r in range(2))
+    assert torch.equal(a["means3D"], b["means3D"]) and torch.equal(a["scales"], b["scales"]) and a["width"] == b["width"] == 64
