@@ -312,6 +312,8 @@ def main():
         """Windows of exactly --steps iterations (barrier + synchronize on both sides, CUDA events between iterations on the
         launching stream, max over ranks per iteration) until --min-time seconds and >= 20 iterations are on record."""
         iters, windows, last, total = [], [], None, 0.0
+        fn()                      # one more untimed step: the first call after a phase change pays one-off allocator / event set-up
+        torch.cuda.synchronize()
         while True:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
             barrier()
