@@ -47,6 +47,10 @@ def stage(verbose: bool = True) -> str | None:
             assert not cmp.diff_files and not cmp.left_only, (it, cmp.diff_files, cmp.left_only)
         else:
             assert filecmp.cmp(src, dst, shallow=False), it
+    with open(os.path.join(OUT, "README_STAGED.txt"), "w") as f:
+        f.write("Byte-identical copies of the reference's own entry points (train.py, render.py, gaussian_renderer/, scene/, utils/, arguments/),\n"
+                "staged by oracle/stage_ref.py from /root/reference for tests/test_gpu_dropin_live.py (the GPU box has no /root/reference).\n"
+                "TEST INFRASTRUCTURE: git-ignored (oracle/_ref/), never part of the repository's history, never imported by the product.\n")
     if verbose:
         print("[stage_ref] staged", ", ".join(ITEMS), "->", OUT)
     return OUT
