@@ -86,6 +86,22 @@ def exchange_sum_(acc: torch.Tensor, group=None, mode: str | None = None) -> tor
     if W == 1:
         return acc
     mode = mode or os.environ.get("RGS_GRAD_EXCHANGE", "dense")
+    if mode == "owner":
+        # Host-side mirror of the device exchange (csrc/rgs_exchange.cu), collective by collective: rows are owned in contiguous
+        # blocks of ceil(P / W); every block is reduced INTO its owner and the owner's sum is then copied to everybody -- one sum per
+        # row, the same bits on every rank.  (The device version moves only the rows that carry something; this one is dense and
+        # exists so that the ownership / reduce / spread logic runs under gloo in the CPU tests.)
+        P = acc.shape[0]
+        rpr = (P + W - 1) // W
+        for owner in range(W):
+            blk = acc[owner * rpr: min(P, (owner + 1) * rpr)]
+            if blk.numel():
+                dist.reduce(blk, dst=dist.get_global_rank(group, owner) if group is not None else owner, op=dist.ReduceOp.SUM, group=group)
+        for owner in range(W):
+            blk = acc[owner * rpr: min(P, (owner + 1) * rpr)]
+            if blk.numel():
+                dist.broadcast(blk, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        return acc
     if mode != "sparse":
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
         return acc

@@ -145,6 +145,7 @@ def _exchange_worker(rank, world, port, tmpdir):
             out[case + "_in"] = acc.clone()
             out[case + "_sparse"] = multigpu.exchange_sum_(acc.clone(), mode="sparse")
             out[case + "_dense"] = multigpu.exchange_sum_(acc.clone(), mode="dense")
+            out[case + "_owner"] = multigpu.exchange_sum_(acc.clone(), mode="owner")   # host mirror of the device-side exchange
             out[case + "_auto"] = multigpu.exchange_sum_(acc.clone())  # default: dense
         torch.save(out, os.path.join(tmpdir, f"exchange{rank}.pt"))
     finally:
@@ -162,6 +163,8 @@ def test_sparse_row_exchange_equals_the_all_reduce(world, tmp_path):
             assert torch.equal(r[case + "_sparse"], res[0][case + "_sparse"])  # same bits on every rank, like an all-reduce
             assert torch.allclose(r[case + "_sparse"].double(), total, rtol=1e-6, atol=1e-6)
             assert torch.allclose(r[case + "_dense"].double(), total, rtol=1e-6, atol=1e-6)
+            assert torch.equal(r[case + "_owner"], res[0][case + "_owner"])    # owner-computed sums: bit-identical on every rank
+            assert torch.allclose(r[case + "_owner"].double(), total, rtol=1e-6, atol=1e-6)
             assert torch.allclose(r[case + "_auto"].double(), total, rtol=1e-6, atol=1e-6)
 
 
